@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the weight-quantization hot path.
+
+Workload (BASELINE.json configs[1]): 4-bit blockwise (blocksize 64) quantize +
+nibble-pack of all Llama-2-7B-shaped decoder linears (32 x {4x[4096,4096],
+2x[11008,4096], [4096,11008]} = 6.476 G fp32 elements, 25.9 GB) on one B200.
+A "step" is one pass over all 226 matrices.
+
+  value     algorithmic GB/s (4.625 B/elem: 4 read + 0.5 packed + 8/64 scale+zp),
+            inputs resident in HBM, the 226 per-matrix launches replayed as one
+            CUDA graph, timed with CUDA events
+  e2e       the same metric through the public API with HOST buffers: pinned
+            host -> device copies of every matrix and device -> host copies of
+            every result inside the timed region
+  roofline  achieved GB/s of the dominant kernel (quantize_rows_tma_kernel)
+            against the measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the C oracle port of the reference algorithm on the host cores
+
+`--impl reference` times the reference's CPU algorithm (oracle port; the
+reference itself is pure Python/torch and does not travel to the GPU box).
+N > 1 (torchrun): every rank quantizes its own 7B-shaped weight set (weak
+scaling, no data-path collective — SURVEY §8(e)).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLAMA2_7B_LAYER = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+N_LAYERS = 32
+BYTES_PER_ELEM = 4.0 + 0.5 + 8.0 / 64.0
+BLOCK = 64
+METRIC = "quantize/dequantize GB/s vs HBM peak (4-bit block-64 quantize+pack, algorithmic bytes)"
+WORKLOAD = "llama2-7b decoder linears, fp32 -> 4-bit block-64 quantize+pack"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def shapes():
+    return LLAMA2_7B_LAYER * N_LAYERS
+
+
+def cpu_sample(threads=None):
+    """One decoder layer (7 matrices, 202 M elements) for the CPU arm."""
+    import numpy as np
+    rng = np.random.default_rng(1234)
+    mats = []
+    for r, c in LLAMA2_7B_LAYER:
+        mats.append((rng.standard_normal(r * c, dtype=np.float32) * np.float32(0.02)))
+    return mats
+
+
+def time_cpu(mats, reps, warmup):
+    from oracle import oracle_c as OC
+    OC.build()
+    elems = sum(m.size for m in mats)
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        for m in mats:
+            OC.quantize4_block_pack(m, BLOCK)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return elems, times, OC.num_threads()
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference algorithm on all host threads."""
+    if rank != 0:
+        return
+    mats = cpu_sample()
+    elems, times, threads = time_cpu(mats, args.steps, args.warmup)
+    t = sum(times) / len(times)
+    value = elems * BYTES_PER_ELEM / t / 1e9
+    sample = "one decoder layer (7 matrices, %d elements) per step" % elems
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "blocksize": BLOCK, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import quanta_b200 as Q
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    shp = shapes()
+    sizes = [r * c for r, c in shp]
+    total = sum(sizes)
+
+    # ---- inputs resident in HBM: one flat fp32 buffer holding all 226 matrices
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    step_fill = 1 << 28
+    for off in range(0, total, step_fill):
+        flat[off:off + step_fill].normal_(0.0, 0.02, generator=gen)
+    views, off = [], 0
+    for (r, c), n in zip(shp, sizes):
+        views.append(flat[off:off + n].view(r, c))
+        off += n
+
+    def step():
+        return [Q.quantize_4bit(v, blocksize=BLOCK, packed=True) for v in views]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # eager warm-up (loads the library, sets kernel attributes), then capture one step
+    outs = step()
+    torch.cuda.synchronize()
+    del outs
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = step()
+    for _ in range(args.warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * total * BYTES_PER_ELEM / (ms * 1e-3) / 1e9
+    per_gpu = total * BYTES_PER_ELEM / (ms * 1e-3) / 1e9
+    launches = args.steps * len(views)
+    del outs, graph
+    torch.cuda.empty_cache()
+
+    # ---- e2e: host buffers -> public API -> host results, copies inside the timed region
+    layer = LLAMA2_7B_LAYER
+    host_in = [torch.empty(r, c, dtype=torch.float32).normal_(0.0, 0.02).pin_memory() for r, c in layer]
+    host_out = [(torch.empty(r * c // 2, dtype=torch.uint8).pin_memory(),
+                 torch.empty(r * c // BLOCK, dtype=torch.float32).pin_memory(),
+                 torch.empty(r * c // BLOCK, dtype=torch.float32).pin_memory()) for r, c in layer]
+    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+    big = max(r * c for r, c in layer)
+    stage = [torch.empty(big, dtype=torch.float32, device=device) for _ in streams]
+
+    def e2e_step():
+        i = 0
+        for _ in range(N_LAYERS):
+            for m, (r, c) in enumerate(layer):
+                s = i % 2
+                with torch.cuda.stream(streams[s]):
+                    d = stage[s][:r * c].view(r, c)
+                    d.copy_(host_in[m], non_blocking=True)
+                    pk, sc, zp = Q.quantize_4bit(d, blocksize=BLOCK, packed=True)
+                    host_out[m][0].copy_(pk, non_blocking=True)
+                    host_out[m][1].copy_(sc, non_blocking=True)
+                    host_out[m][2].copy_(zp, non_blocking=True)
+                i += 1
+
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * total * BYTES_PER_ELEM / e2e_s / 1e9
+    h2d = total * 4
+    d2h = total // 2 + 2 * (total // BLOCK) * 4
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample = one decoder layer
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        mats = cpu_sample()
+        elems, times, threads = time_cpu(mats, 3, 1)
+        tcpu = min(times)
+        cpu = {"value": elems * BYTES_PER_ELEM / tcpu / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": "one decoder layer (7 matrices, %d elements), best of 3; C oracle port, OpenMP" % elems}
+
+    peak, which = peaks()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+            "config": {"workload": WORKLOAD, "elements_per_gpu": total, "matrices": len(views), "blocksize": BLOCK,
+                       "bytes_per_element": BYTES_PER_ELEM, "l2": "inputs (25.9 GB) larger than L2",
+                       "launch": "226 per-matrix launches replayed as one CUDA graph",
+                       "parallelism": "replicated weight sets, one per GPU, no collective"},
+            "roofline": {"bound": "hbm", "kernel": "quantize_rows_tma_kernel<float,4,pack,A,blockwise>",
+                         "achieved": per_gpu, "peak": peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                         "unit": "GB/s", "frac": per_gpu / peak, "traffic": None},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "note": "pinned host buffers, 2 streams, H2D + quantize + D2H per matrix"},
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/*
+ * quanta_b200 — C ABI of the B200 (sm_100a) weight-quantization hot path.
+ *
+ * This is the drop-in boundary: a plain C shared library (libquanta_b200.so)
+ * that a binding on the reference side (ctypes from
+ * Quanta/backends/cuda/quantization.py) calls with raw
+ * device pointers.  Every entry point is
+ *   - non-allocating (the caller owns inputs, outputs and the workspace),
+ *   - asynchronous on the caller-supplied cudaStream_t (passed as void*),
+ *   - non-throwing: returns 0 on success, a negative QUANTA_E* code for
+ *     argument errors, or a positive cudaError_t from the launch.
+ * No host synchronisation happens inside any call: the reference's host-side
+ * decisions (`if max_val == min_val`, `torch.allclose(...)`) are evaluated on
+ * the device.
+ *
+ * file:line citations are relative to the reference tree (ved1beta/Quanta).
+ */
+#ifndef QUANTA_B200_H
+#define QUANTA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QUANTA_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define QUANTA_API __attribute__((visibility("default")))
+#else
+#define QUANTA_API
+#endif
+
+/* reduction granularity of scale / zero_point */
+#define QUANTA_MODE_TENSOR 0   /* per_channel=False : one scale for the whole tensor          */
+#define QUANTA_MODE_DIM0   1   /* per_channel=True  : min/max over dim 0 -> one scale per column */
+#define QUANTA_MODE_BLOCK  2   /* blockwise: per_channel applied to x.reshape(-1, block).t()    */
+
+/* element types of floating-point buffers */
+#define QUANTA_F32  0
+#define QUANTA_F16  1
+#define QUANTA_BF16 2
+
+/* error codes (negative); positive return values are cudaError_t */
+#define QUANTA_OK              0
+#define QUANTA_EINVAL         -1   /* bad argument (null pointer, bits not 4/8, n % block != 0 ...) */
+#define QUANTA_EUNSUPPORTED   -2   /* combination not implemented                                    */
+#define QUANTA_EWORKSPACE     -3   /* workspace too small, see quanta_workspace_bytes                */
+#define QUANTA_EDRIVER        -4   /* CUDA driver entry point (tensor-map encode) unavailable        */
+
+/* workspace queries */
+#define QUANTA_OP_QUANTIZE_AFFINE    0
+#define QUANTA_OP_BACKEND_QUANTIZE   1
+#define QUANTA_OP_BACKEND_DEQUANTIZE 2
+#define QUANTA_OP_GEMM               3
+#define QUANTA_OP_INT8_OUTLIER       4
+
+QUANTA_API int         quanta_abi_version(void);
+QUANTA_API const char* quanta_error_string(int code);
+
+/* Bytes of device workspace needed by `op` on a [rows, cols] problem
+ * (for QUANTA_OP_GEMM / INT8_OUTLIER: rows = M, cols = N).  Always >= 256. */
+QUANTA_API size_t quanta_workspace_bytes(int op, int64_t rows, int64_t cols);
+
+/* ---- convention A: Quanta/functional/quantization.py "linear" -------------
+ *
+ * Replaces quantize_8bit / quantize_4bit -> quantize_{8,4}bit_linear
+ * (functional/quantization.py:7-31, :73-99, :185-210):
+ *     mn, mx = min, max         (all elements | over dim 0 | per block)
+ *     if mx == mn: mx = mn + 1e-6
+ *     scale = (mx - mn) / L ; zero_point = mn            (L = 255 or 15)
+ *     q = clamp(round((x - mn) / scale), 0, L)           -> uint8
+ * x is a contiguous [rows, cols] tensor (any shape flattened to rows x cols;
+ * for TENSOR and BLOCK only rows*cols matters).  BLOCK: (rows*cols) % block
+ * must be 0; block b covers flat elements [b*block, (b+1)*block).
+ * Outputs: q_out uint8, one code per byte (values 0..L), or — when
+ * pack4 != 0 (bits == 4 only) — nibble-packed exactly as pack_4bit_tensor
+ * (utils/utils.py:23-35: even index -> low nibble, one zero pad if odd);
+ * scale_out / zp_out float32: 1 value (TENSOR), cols values (DIM0),
+ * rows*cols/block values (BLOCK).  x_dtype F16/BF16 inputs are widened to
+ * fp32 first and then follow the fp32 arithmetic (declared deviation: the
+ * reference would round every intermediate to the 16-bit type).          */
+QUANTA_API int quanta_quantize_affine(const void* x, int x_dtype, int64_t rows, int64_t cols,
+                           int mode, int64_t block, int bits, int pack4,
+                           uint8_t* q_out, float* scale_out, float* zp_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces dequantize_8bit / dequantize_4bit, quant_type="linear"
+ * (functional/quantization.py:33-38, :53-58): out = q.float() * scale + zp,
+ * multiply and add rounded separately.  packed4 != 0: q holds nibble-packed
+ * codes (P1 layout) and rows*cols counts CODES.  out_dtype F32 is the
+ * reference behaviour; F16/BF16 round the fp32 result once more.          */
+QUANTA_API int quanta_dequantize_affine(const uint8_t* q, int packed4, int64_t rows, int64_t cols,
+                             int mode, int64_t block, const float* scale, const float* zp,
+                             void* out, int out_dtype, void* stream);
+
+/* ---- 4-bit nibble pack / unpack: Quanta/utils/utils.py:23-48 -------------
+ * pack:   packed[i] = q[2i] | (q[2i+1] << 4) in uint8 arithmetic, one zero
+ *         pad if n is odd; inputs > 15 are not masked (reference behaviour).
+ *         packed holds (n+1)/2 bytes.
+ * unpack: out[2i] = b & 0xF, out[2i+1] = b >> 4; out holds 2*nbytes codes. */
+QUANTA_API int quanta_pack4(const uint8_t* q, int64_t n, uint8_t* packed, void* stream);
+QUANTA_API int quanta_unpack4(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream);
+
+/* ---- convention B: Quanta/backends/cpu/quantization.py -------------------
+ *
+ * Replaces quantize_8bit_cpu / quantize_4bit_cpu (:10-59, :86-135), i.e. the
+ * semantics quantize_{8,4}bit_cuda must have behind
+ * Quanta/backends/__init__.py:61,105.  per_channel reduces over dim 0 of the
+ * [rows, cols] tensor.  symmetric: scale = rcp(absmax)*Q, zp = 0,
+ * q = clamp(round(x*scale), -Q, Q) + OFF; asymmetric: scale = rcp(mx-mn)*L,
+ * zp = round(-mn*scale), q = clamp(round(x*scale + zp), 0, L).  If
+ * allclose(min, max) holds for ALL channels the reference's early-out is
+ * reproduced: codes 0, scale 1, zp = min.  scale_out / zp_out: 1 or cols.  */
+QUANTA_API int quanta_backend_quantize(const void* x, int x_dtype, int64_t rows, int64_t cols,
+                            int per_channel, int symmetric, int bits,
+                            uint8_t* q_out, float* scale_out, float* zp_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces dequantize_8bit_cpu / dequantize_4bit_cpu (:61-84, :137-160):
+ * if allclose(zp, 0) for all channels, q' = int8(q) - OFF else q' = q;
+ * out = (q'.float() - zp) / scale (true divide).  nchan = 1 or cols.       */
+QUANTA_API int quanta_backend_dequantize(const uint8_t* q, int64_t rows, int64_t cols, int64_t nchan, int bits,
+                              const float* scale, const float* zp, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- dequantize-then-matmul behind Quanta/nn/linear.py -------------------
+ *
+ * Replaces the placeholder F.linear in Linear4bit.forward (nn/linear.py:81-83)
+ * and Linear8bitLt.forward (:43-45):  y[M,N] = x[M,K] . dequant(Wq)[N,K]^T + bias
+ * with Wq in convention A, blockwise along K (block | K, block % 64 == 0):
+ *   bits 8: wq uint8 [N, K];  bits 4: wq nibble-packed [N, K/2] (P1 layout)
+ *   scale, zp float32 [N, K/block].
+ * x, y, bias are `act_dtype` (F16 or BF16); accumulation is fp32 on the
+ * tcgen05 tensor cores.  bias may be NULL.                                 */
+QUANTA_API int quanta_gemm_wna16(const void* x, int act_dtype, const uint8_t* wq, int bits,
+                      const float* scale, const float* zp, int64_t block,
+                      const void* bias, void* y, int64_t M, int64_t N, int64_t K,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* LLM.int8()-style outlier-split matmul for Linear8bitLt.threshold
+ * (nn/linear.py:20,25; unused by the reference — semantics defined by this
+ * repository, see oracle/oracle_np.py:int8_outlier_matmul).
+ *   qw int8 [N,K] row-wise symmetric codes, cw float32 [N] multipliers
+ *   (127/absmax), x/y/bias `act_dtype`.                                    */
+QUANTA_API int quanta_int8_outlier_matmul(const void* x, int act_dtype, const int8_t* qw, const float* cw,
+                               float threshold, const void* bias, void* y,
+                               int64_t M, int64_t N, int64_t K,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUANTA_B200_H */

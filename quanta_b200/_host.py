@@ -1,0 +1,47 @@
+"""Shared host-side plumbing: device checks, dtype codes, stream, workspace."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DTYPE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+_workspaces = {}
+
+
+def require_cuda(t, name="tensor"):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"quanta_b200 is the CUDA backend of this path and has no CPU fallback: "
+                           f"{name} is on {t.device}")
+
+
+def dtype_code(t):
+    try:
+        return _DTYPE[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected float32, float16 or bfloat16") from None
+
+
+def stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def workspace(device, nbytes):
+    """Per (device, stream) scratch buffer, grown on demand.  Reuse is safe
+    because every kernel that touches it is ordered on that stream."""
+    key = (device.index, stream_ptr(device))
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def rows_cols(t):
+    """[rows, cols] view of a contiguous tensor: dim 0 x everything else."""
+    if t.dim() == 0:
+        return 1, 1
+    rows = t.shape[0]
+    return rows, (t.numel() // rows if rows else 0)

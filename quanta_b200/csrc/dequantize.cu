@@ -1,0 +1,215 @@
+// Dequantize kernels (rows A4, B2 of SURVEY §8) and their C-ABI entry points.
+//
+// Output-bandwidth bound (1 B in, 4 B out per code).  Every warp store is a
+// fully coalesced 512-byte STG.128 sweep; codes are widened with one PRMT into
+// the mantissa of 2^23 (exact u8 -> fp32, no I2F), then the reference's two
+// separately rounded operations are applied with explicit _rn intrinsics.
+#include "common.cuh"
+
+namespace quanta {
+
+enum DqConv : int { kDqA = 0, kDqB = 1 };
+
+// exact float(byte k of w)
+template <int K>
+__device__ __forceinline__ float byte_to_f32(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(0x7540u + K));
+    return __fsub_rn(__uint_as_float(r), 8388608.0f);
+}
+
+struct DqParam { float s, z; };
+
+// conv A: RN(RN(q*s) + z)            (functional/quantization.py:38,58)
+// conv B: RN(RN(q' - z) / s), q' = int8(q) - OFF when `sym`   (backends/cpu/quantization.py:80-84)
+template <int CONV>
+__device__ __forceinline__ float dq_value(float qf, const DqParam& p, bool sym, float off) {
+    if (CONV == kDqA) return __fadd_rn(__fmul_rn(qf, p.s), p.z);
+    if (sym) {
+        // ((q - OFF + 128) mod 256) - 128: the reference's int8 arithmetic wraps
+        float v = qf - off;                    // exact small integers in [-128, 247]
+        v = v > 127.0f ? v - 256.0f : v;
+        qf = v;
+    }
+    return __fdiv_rn(__fsub_rn(qf, p.z), p.s);
+}
+
+template <typename OUT> __device__ __forceinline__ void store4(OUT* dst, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* dst, float a, float b, float c, float d) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(a, b, c, d));
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* dst, float a, float b, float c, float d) {
+    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 v; v.x = *reinterpret_cast<uint32_t*>(&lo); v.y = *reinterpret_cast<uint32_t*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(dst), v);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 v; v.x = *reinterpret_cast<uint32_t*>(&lo); v.y = *reinterpret_cast<uint32_t*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(dst), v);
+}
+template <typename OUT> __device__ __forceinline__ OUT from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 codes starting at element i (i % 4 == 0) as one 32-bit word of bytes.
+template <bool PACKED>
+__device__ __forceinline__ uint32_t load_codes4(const uint8_t* q, int64_t i) {
+    if (!PACKED) return __ldcs(reinterpret_cast<const unsigned int*>(q + i));
+    uint32_t h = __ldcs(reinterpret_cast<const unsigned short*>(q + (i >> 1)));
+    // [n0 n1 | n2 n3] nibbles -> bytes n0, n1, n2, n3
+    return (h & 0x000Fu) | ((h & 0x00F0u) << 4) | ((h & 0x0F00u) << 8) | ((h & 0xF000u) << 12);
+}
+
+// TENSOR / BLOCK: flat sweep, 4 codes per thread per step, params per step.
+template <typename OUT, bool PACKED, int CONV>
+__global__ void __launch_bounds__(256) dequant_flat_kernel(const uint8_t* __restrict__ q, int64_t n4, int block_shift,
+                                                           int64_t block, const float* __restrict__ scale,
+                                                           const float* __restrict__ zp, OUT* __restrict__ out,
+                                                           const int* __restrict__ flag, float off) {
+    const bool sym = CONV == kDqB && flag[0] != 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+        const int64_t i = g * 4;
+        uint32_t w = load_codes4<PACKED>(q, i);
+        int64_t b = block == 0 ? 0 : (block_shift >= 0 ? (i >> block_shift) : (i / block));
+        DqParam p{__ldg(scale + b), __ldg(zp + b)};
+        store4<OUT>(out + i, dq_value<CONV>(byte_to_f32<0>(w), p, sym, off), dq_value<CONV>(byte_to_f32<1>(w), p, sym, off),
+                    dq_value<CONV>(byte_to_f32<2>(w), p, sym, off), dq_value<CONV>(byte_to_f32<3>(w), p, sym, off));
+    }
+}
+
+// DIM0: thread owns 4 consecutive columns and walks down a chunk of rows.
+template <typename OUT, bool PACKED, int CONV>
+__global__ void __launch_bounds__(128) dequant_dim0_kernel(const uint8_t* __restrict__ q, int64_t rows, int64_t cols,
+                                                           int rows_per_chunk, const float* __restrict__ scale,
+                                                           const float* __restrict__ zp, OUT* __restrict__ out,
+                                                           const int* __restrict__ flag, float off) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= cols) return;
+    const bool sym = CONV == kDqB && flag[0] != 0;
+    DqParam p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { p[j].s = scale[c + j]; p[j].z = zp[c + j]; }
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = min(rows, r0 + rows_per_chunk);
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t i = r * cols + c;
+        uint32_t w = load_codes4<PACKED>(q, i);
+        store4<OUT>(out + i, dq_value<CONV>(byte_to_f32<0>(w), p[0], sym, off), dq_value<CONV>(byte_to_f32<1>(w), p[1], sym, off),
+                    dq_value<CONV>(byte_to_f32<2>(w), p[2], sym, off), dq_value<CONV>(byte_to_f32<3>(w), p[3], sym, off));
+    }
+}
+
+// Any shape / alignment: one element per thread.  chan(i) = 0 | i / block | i % cols.
+template <typename OUT, bool PACKED, int CONV>
+__global__ void __launch_bounds__(256) dequant_generic_kernel(const uint8_t* __restrict__ q, int64_t start, int64_t n,
+                                                              int mode, int64_t p, const float* __restrict__ scale,
+                                                              const float* __restrict__ zp, OUT* __restrict__ out,
+                                                              const int* __restrict__ flag, float off) {
+    const int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool sym = CONV == kDqB && flag[0] != 0;
+    uint32_t code = PACKED ? ((q[i >> 1] >> ((i & 1) * 4)) & 0xFu) : q[i];
+    const int64_t ch = mode == QUANTA_MODE_TENSOR ? 0 : (mode == QUANTA_MODE_BLOCK ? i / p : i % p);
+    DqParam pr{scale[ch], zp[ch]};
+    out[i] = from_f32<OUT>(dq_value<CONV>((float)code, pr, sym, off));
+}
+
+// B2's host-side `torch.allclose(zero_point, 0)` evaluated on the device:
+// flag = all(|zp| <= 1e-8)  (NaN -> not close).
+__global__ void __launch_bounds__(256) zp_allclose_zero_kernel(const float* __restrict__ zp, int64_t nchan, int* flag) {
+    int ok = 1;
+    for (int64_t i = threadIdx.x; i < nchan; i += blockDim.x) {
+        float a = fabsf(zp[i]);
+        ok &= (zp[i] == 0.0f) || (a <= 1e-8f);
+    }
+    ok = __syncthreads_and(ok);
+    if (threadIdx.x == 0) flag[0] = ok;
+}
+
+static int shift_of(int64_t v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((int64_t(1) << s) < v) ++s;
+    return s;
+}
+
+template <typename OUT, bool PACKED, int CONV>
+static int dequant_launch(const uint8_t* q, int64_t rows, int64_t cols, int mode, int64_t block, const float* scale,
+                          const float* zp, OUT* out, const int* flag, float off, cudaStream_t st) {
+    const int64_t n = rows * cols;
+    const uintptr_t qa = reinterpret_cast<uintptr_t>(q), oa = reinterpret_cast<uintptr_t>(out);
+    const bool ptr_ok = (qa % (PACKED ? 2 : 4) == 0) && (oa % (4 * sizeof(OUT)) == 0);
+    if (mode == QUANTA_MODE_DIM0 && ptr_ok && cols % 4 == 0) {
+        int chunks = (int)((rows + 31) / 32);
+        if (chunks > 2048) chunks = 2048;
+        const int rpc = (int)((rows + chunks - 1) / chunks);
+        chunks = (int)((rows + rpc - 1) / rpc);
+        dim3 g((unsigned)((cols / 4 + 127) / 128), chunks);
+        dequant_dim0_kernel<OUT, PACKED, CONV><<<g, 128, 0, st>>>(q, rows, cols, rpc, scale, zp, out, flag, off);
+        return cuda_status(cudaGetLastError());
+    }
+    int64_t done = 0;
+    if (mode != QUANTA_MODE_DIM0 && ptr_ok && (mode == QUANTA_MODE_TENSOR || block % 4 == 0)) {
+        const int64_t n4 = n / 4;
+        if (n4 > 0) {
+            int64_t want = (n4 + 255) / 256;
+            int64_t cap = (int64_t)kNumSMs * 8 * 4;
+            dequant_flat_kernel<OUT, PACKED, CONV><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
+                q, n4, shift_of(block), mode == QUANTA_MODE_TENSOR ? 0 : block, scale, zp, out, flag, off);
+        }
+        done = n4 * 4;
+    }
+    if (done < n) {
+        const int64_t rest = n - done;
+        dequant_generic_kernel<OUT, PACKED, CONV><<<(unsigned)((rest + 255) / 256), 256, 0, st>>>(
+            q, done, n, mode, mode == QUANTA_MODE_BLOCK ? block : cols, scale, zp, out, flag, off);
+    }
+    return cuda_status(cudaGetLastError());
+}
+
+template <bool PACKED, int CONV>
+static int dequant_dtype(const uint8_t* q, int64_t rows, int64_t cols, int mode, int64_t block, const float* scale,
+                         const float* zp, void* out, int out_dtype, const int* flag, float off, cudaStream_t st) {
+    switch (out_dtype) {
+        case QUANTA_F32:
+            return dequant_launch<float, PACKED, CONV>(q, rows, cols, mode, block, scale, zp, static_cast<float*>(out), flag, off, st);
+        case QUANTA_F16:
+            return dequant_launch<__half, PACKED, CONV>(q, rows, cols, mode, block, scale, zp, static_cast<__half*>(out), flag, off, st);
+        case QUANTA_BF16:
+            return dequant_launch<__nv_bfloat16, PACKED, CONV>(q, rows, cols, mode, block, scale, zp,
+                                                               static_cast<__nv_bfloat16*>(out), flag, off, st);
+    }
+    return QUANTA_EINVAL;
+}
+
+}  // namespace quanta
+
+using namespace quanta;
+
+extern "C" int quanta_dequantize_affine(const uint8_t* q, int packed4, int64_t rows, int64_t cols, int mode,
+                                        int64_t block, const float* scale, const float* zp, void* out, int out_dtype,
+                                        void* stream) {
+    if (!q || !scale || !zp || !out || rows <= 0 || cols <= 0) return QUANTA_EINVAL;
+    if (mode < QUANTA_MODE_TENSOR || mode > QUANTA_MODE_BLOCK) return QUANTA_EINVAL;
+    if (mode == QUANTA_MODE_BLOCK && (block <= 0 || (rows * cols) % block != 0)) return QUANTA_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return packed4 ? dequant_dtype<true, kDqA>(q, rows, cols, mode, block, scale, zp, out, out_dtype, nullptr, 0.f, st)
+                   : dequant_dtype<false, kDqA>(q, rows, cols, mode, block, scale, zp, out, out_dtype, nullptr, 0.f, st);
+}
+
+extern "C" int quanta_backend_dequantize(const uint8_t* q, int64_t rows, int64_t cols, int64_t nchan, int bits,
+                                         const float* scale, const float* zp, float* out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    if (!q || !scale || !zp || !out || !workspace || rows <= 0 || cols <= 0) return QUANTA_EINVAL;
+    if ((bits != 8 && bits != 4) || (nchan != 1 && nchan != cols)) return QUANTA_EINVAL;
+    if (workspace_bytes < 256) return QUANTA_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* flag = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(workspace) + 15) & ~uintptr_t(15));
+    zp_allclose_zero_kernel<<<1, 256, 0, st>>>(zp, nchan, flag);
+    const int mode = nchan == 1 ? QUANTA_MODE_TENSOR : QUANTA_MODE_DIM0;
+    return dequant_dtype<false, kDqB>(q, rows, cols, mode, 0, scale, zp, out, QUANTA_F32, flag, bits == 8 ? 128.f : 8.f, st);
+}

@@ -1,0 +1,763 @@
+// Quantize kernels (rows A1-A3, B1 of SURVEY §8) and their C-ABI entry points.
+//
+// Hot kernel: quantize_rows_tma_kernel — a persistent, warp-specialised stream:
+//   * one producer warp feeds a 3-stage shared-memory ring with 32 KB TMA tiles
+//     (cp.async.bulk.tensor, 256 rows x 128 B, SWIZZLE_128B, L2 evict-first),
+//   * 256 consumer threads each own one 32-element row: the swizzle makes the
+//     8 x LDS.128 of a row bank-conflict free and leaves the row in natural
+//     order in registers, so a 64-element block is one shuffle away and the
+//     packed codes leave as ONE aligned 128-bit store per thread.
+// Arithmetic is bit-exact with the reference's eager torch chain (see
+// common.cuh: affine_params / affine_quotient / code_bits).
+#include "common.cuh"
+
+namespace quanta {
+
+// --------------------------------------------------------------------------
+// conventions
+// --------------------------------------------------------------------------
+enum Conv : int { kConvA = 0, kConvBSym = 1, kConvBAsym = 2 };
+
+// Per-group parameters as the element loop needs them.
+struct ElemParams {
+    // conv A: a = mn, s = scale, r = rcp (0 -> slow divide)
+    // conv B: s = scale (multiplier), a = zp
+    float a, s, r;
+};
+
+template <int CONV, bool ASSUME_FAST = false>
+__device__ __forceinline__ uint32_t elem_code_bits(float x, const ElemParams& p, float L, float Q) {
+    if (CONV == kConvA) {
+        AffineParams ap{p.a, p.s, p.r, ASSUME_FAST || p.r != 0.0f};
+        return code_bits(affine_quotient(x, ap), L);
+    } else if (CONV == kConvBSym) {
+        // q = clamp(round(x*scale), -Q, Q) (+OFF added by the packer); NaN -> 0
+        float t = __fmul_rn(x, p.s);
+        float c = fminf(fmaxf(t, -Q), Q);
+        c = (t != t) ? 0.0f : c;
+        return __float_as_uint(__fadd_rn(c, kMagic));
+    } else {
+        float t = __fadd_rn(__fmul_rn(x, p.s), p.a);
+        return code_bits(t, L);
+    }
+}
+
+// Pack N code words (kMagicBits + code) into bytes / nibbles with a Horner
+// chain of IMADs; the magic offsets add up to a compile-time constant.
+template <int CONV, int BITS>
+__device__ __forceinline__ uint32_t pack_bytes4(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3) {
+    constexpr uint32_t off = (CONV == kConvBSym) ? (BITS == 8 ? 128u : 8u) : 0u;
+    constexpr uint32_t k = (kMagicBits - off) * 0x01010101u;
+    uint32_t acc = u3;
+    acc = acc * 256u + u2;
+    acc = acc * 256u + u1;
+    acc = acc * 256u + u0;
+    return acc - k;
+}
+template <int CONV>
+__device__ __forceinline__ uint32_t pack_nibbles8(const uint32_t* u) {
+    constexpr uint32_t off = (CONV == kConvBSym) ? 8u : 0u;
+    constexpr uint32_t k = (kMagicBits - off) * 0x11111111u;
+    uint32_t acc = u[7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i) acc = acc * 16u + u[i];
+    return acc - k;
+}
+
+// Parameters from (mn, mx) for the three conventions.  For conv B `close`
+// returns torch.isclose(mn, mx) (backends/cpu/quantization.py:38).
+__device__ __forceinline__ bool isclose_f32(float a, float b) {
+    if (a == b) return true;
+    float allowed = __fadd_rn(1e-8f, fabsf(__fmul_rn(1e-5f, b)));
+    float actual = fabsf(__fsub_rn(a, b));
+    return (fabsf(actual) <= 3.402823466e38f) && actual <= allowed;
+}
+
+template <int CONV>
+__device__ __forceinline__ void group_params(float mn, float mx, int bits, float* scale, float* zp, float* rcp,
+                                             bool* close) {
+    const float L = bits == 8 ? 255.0f : 15.0f, Q = bits == 8 ? 127.0f : 7.0f;
+    if (CONV == kConvA) {
+        AffineParams p = affine_params(mn, mx, L);
+        *scale = p.scale; *zp = p.mn; *rcp = p.rcp; *close = false;
+    } else {
+        *close = isclose_f32(mn, mx);
+        if (CONV == kConvBSym) {
+            float am = max_nan(fabsf(mn), fabsf(mx));
+            *scale = __fmul_rn(__frcp_rn(am), Q);          // int / Tensor == reciprocal * int
+            *zp = 0.0f;
+        } else {
+            float s = __fmul_rn(__frcp_rn(__fsub_rn(mx, mn)), L);
+            *scale = s;
+            *zp = rintf(__fmul_rn(-mn, s));
+        }
+        *rcp = 0.0f;
+    }
+}
+
+// --------------------------------------------------------------------------
+// workspace layout (floats): [0] early-out flag (int) | [64 ...] rcp per channel
+// | partial min / max
+// --------------------------------------------------------------------------
+constexpr int kWsHeaderFloats = 64;
+constexpr int kMaxPartialCtas = kNumSMs * 8;
+constexpr int kMaxDim0Chunks = 64;
+
+// --------------------------------------------------------------------------
+// 1. min/max reductions
+// --------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_tensor_partial_kernel(const T* __restrict__ x, int64_t n,
+                                                                    float* __restrict__ pmin,
+                                                                    float* __restrict__ pmax) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    float mn = to_f32(x[0]), mx = mn;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    int64_t nvec = aligned ? n / VEC : 0;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    int64_t i = tid;
+    // 4 independent 128-bit loads in flight per thread
+    for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(xv + i + k * nthreads);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const T* e = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { float f = to_f32(e[j]); mn = min_nan(mn, f); mx = max_nan(mx, f); }
+        }
+    }
+    for (; i < nvec; i += nthreads) {
+        uint4 v = __ldg(xv + i);
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { float f = to_f32(e[j]); mn = min_nan(mn, f); mx = max_nan(mx, f); }
+    }
+    for (int64_t j = nvec * VEC + tid; j < n; j += nthreads) {
+        float f = to_f32(x[j]); mn = min_nan(mn, f); mx = max_nan(mx, f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = min_nan(mn, smn[w]); mx = max_nan(mx, smx[w]); }
+        pmin[blockIdx.x] = mn; pmax[blockIdx.x] = mx;
+    }
+}
+
+template <int CONV>
+__global__ void __launch_bounds__(256) minmax_tensor_finalize_kernel(const float* __restrict__ pmin,
+                                                                     const float* __restrict__ pmax, int nparts,
+                                                                     int bits, float* scale_out, float* zp_out,
+                                                                     float* ws) {
+    float mn = pmin[0], mx = pmax[0];
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { mn = min_nan(mn, pmin[i]); mx = max_nan(mx, pmax[i]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = min_nan(mn, smn[w]); mx = max_nan(mx, smx[w]); }
+        float s, z, r; bool close;
+        group_params<CONV>(mn, mx, bits, &s, &z, &r, &close);
+        if (CONV != kConvA && close) { s = 1.0f; z = mn; }      // early-out: zeros, ones_like(min), min
+        scale_out[0] = s; zp_out[0] = z;
+        ws[kWsHeaderFloats] = r;
+        reinterpret_cast<int*>(ws)[0] = (CONV != kConvA && close) ? 1 : 0;
+    }
+}
+
+// dim 0: thread owns 4 consecutive columns, blockIdx.y owns a chunk of rows.
+template <typename T>
+__global__ void __launch_bounds__(128) minmax_dim0_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
+                                                                  int rows_per_chunk, float* __restrict__ pmin,
+                                                                  float* __restrict__ pmax) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = min(rows, r0 + rows_per_chunk);
+    float mn[4], mx[4];
+    auto load4 = [&](int64_t r, float* f) {
+        if (sizeof(T) == 4) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + r * cols + c));
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
+            uint2 v = __ldg(reinterpret_cast<const uint2*>(x + r * cols + c));
+            const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = to_f32(e[j]);
+        }
+    };
+    load4(r0, mn);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mx[j] = mn[j];
+    int64_t r = r0 + 1;
+    for (; r + 3 < r1; r += 4) {
+        float f[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) load4(r + k, f[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mn[j] = min_nan(mn[j], f[k][j]); mx[j] = max_nan(mx[j], f[k][j]); }
+    }
+    for (; r < r1; ++r) {
+        float f[4]; load4(r, f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mn[j] = min_nan(mn[j], f[j]); mx[j] = max_nan(mx[j], f[j]); }
+    }
+    float4* om = reinterpret_cast<float4*>(pmin + (int64_t)blockIdx.y * cols + c);
+    float4* ox = reinterpret_cast<float4*>(pmax + (int64_t)blockIdx.y * cols + c);
+    *om = make_float4(mn[0], mn[1], mn[2], mn[3]);
+    *ox = make_float4(mx[0], mx[1], mx[2], mx[3]);
+}
+
+// generic dim-0 partial (any cols / alignment): one thread per column.
+template <typename T>
+__global__ void __launch_bounds__(128) minmax_dim0_partial_generic_kernel(const T* __restrict__ x, int64_t rows,
+                                                                          int64_t cols, int rows_per_chunk,
+                                                                          float* __restrict__ pmin,
+                                                                          float* __restrict__ pmax) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = min(rows, r0 + rows_per_chunk);
+    float mn = to_f32(x[r0 * cols + c]), mx = mn;
+    for (int64_t r = r0 + 1; r < r1; ++r) { float f = to_f32(x[r * cols + c]); mn = min_nan(mn, f); mx = max_nan(mx, f); }
+    pmin[(int64_t)blockIdx.y * cols + c] = mn;
+    pmax[(int64_t)blockIdx.y * cols + c] = mx;
+}
+
+// Reduce the row-chunk partials of each column and emit its parameters; conv B
+// also needs "allclose for ALL channels": every thread ANDs into ws[0]
+// (pre-set to 1 by minmax_dim0_flag_init).
+__global__ void dim0_flag_init_kernel(float* ws, int value) { reinterpret_cast<int*>(ws)[0] = value; }
+
+template <int CONV>
+__global__ void __launch_bounds__(128) minmax_dim0_finalize_kernel(const float* __restrict__ pmin,
+                                                                   const float* __restrict__ pmax, int nchunks,
+                                                                   int64_t cols, int bits, float* scale_out,
+                                                                   float* zp_out, float* ws) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool close = true;
+    if (c < cols) {
+        float mn = pmin[c], mx = pmax[c];
+        for (int k = 1; k < nchunks; ++k) { mn = min_nan(mn, pmin[k * cols + c]); mx = max_nan(mx, pmax[k * cols + c]); }
+        float s, z, r;
+        group_params<CONV>(mn, mx, bits, &s, &z, &r, &close);
+        scale_out[c] = s; zp_out[c] = z;
+        ws[kWsHeaderFloats + c] = (CONV == kConvA) ? r : mn;      // conv B keeps min for the early-out
+    }
+    if (CONV != kConvA) {
+        int all = __syncthreads_and(close ? 1 : 0);
+        if (threadIdx.x == 0 && !all) atomicAnd(reinterpret_cast<int*>(ws), 0);
+    }
+}
+
+// conv B early-out for per_channel: scale = 1, zp = min for every channel.
+__global__ void dim0_earlyout_params_kernel(int64_t cols, float* scale_out, float* zp_out, const float* ws) {
+    if (reinterpret_cast<const int*>(ws)[0] == 0) return;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < cols) { scale_out[c] = 1.0f; zp_out[c] = ws[kWsHeaderFloats + c]; }
+}
+
+// --------------------------------------------------------------------------
+// 2. the streaming TMA kernel (BLOCK and TENSOR modes)
+// --------------------------------------------------------------------------
+constexpr int kRowElems = 32;          // elements owned by one consumer thread
+constexpr int kTileRows = 256;         // rows (= consumer threads) per TMA tile
+constexpr int kStages = 3;
+constexpr int kConsumerWarps = kTileRows / 32;
+constexpr int kTmaThreads = kTileRows + 32;
+
+template <typename T> struct RowLayout {
+    static constexpr int kRowBytes = kRowElems * sizeof(T);            // 128 (fp32) or 64 (16-bit)
+    static constexpr int kChunks = kRowBytes / 16;
+    static constexpr int kTileBytes = kTileRows * kRowBytes;
+    // physical 16-byte chunk of logical chunk j in row r under the TMA swizzle
+    __device__ static __forceinline__ int swz(int r, int j) {
+        return sizeof(T) == 4 ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));
+    }
+};
+
+template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_rows, int lanes_per_block,
+                         uint8_t* __restrict__ q_out, float* __restrict__ scale_out, float* __restrict__ zp_out,
+                         const float* __restrict__ ws) {
+    using RL = RowLayout<T>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===== producer warp: one lane streams tiles into the ring =====
+        if (lane == 0) {
+            prefetch_tensormap(&tmap);
+            const uint64_t policy = policy_evict_first();
+            int i = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], RL::kTileBytes);
+                const int64_t tt = BLOCKWISE ? t : n_tiles - 1 - t;   // 2nd pass: newest-in-L2 first
+                tma_load_2d(smem + s * RL::kTileBytes, &tmap, &full_bar[s], 0, (int32_t)(tt * kTileRows), policy);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread `tid` owns row `tid` of every tile =====
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    constexpr float Q = BITS == 8 ? 127.0f : 7.0f;
+    ElemParams gp{0.f, 1.f, 0.f};
+    bool early = false;
+    if (!BLOCKWISE) {   // TENSOR mode: parameters were produced by the finalize kernel
+        gp.s = scale_out[0];
+        gp.a = zp_out[0];
+        gp.r = ws[kWsHeaderFloats];
+        early = (CONV != kConvA) && reinterpret_cast<const int*>(ws)[0] != 0;
+    }
+
+    int i = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+
+        float v[kRowElems];
+        const uint8_t* row = smem + s * RL::kTileBytes + tid * RL::kRowBytes;
+#pragma unroll
+        for (int j = 0; j < RL::kChunks; ++j) {
+            uint4 c = *reinterpret_cast<const uint4*>(row + (RL::swz(tid, j) << 4));
+            if (sizeof(T) == 4) {
+                v[4 * j + 0] = __uint_as_float(c.x); v[4 * j + 1] = __uint_as_float(c.y);
+                v[4 * j + 2] = __uint_as_float(c.z); v[4 * j + 3] = __uint_as_float(c.w);
+            } else {
+                const T* e = reinterpret_cast<const T*>(&c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * j + k] = to_f32(e[k]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);     // stage can be refilled while we compute
+
+        const int64_t grow = (BLOCKWISE ? t : n_tiles - 1 - t) * kTileRows + tid;      // global row
+        if (BLOCKWISE) {
+            float m0[4], m1[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { m0[k] = v[k]; m1[k] = v[k]; }
+#pragma unroll
+            for (int k = 4; k < kRowElems; ++k) { m0[k & 3] = min_nan(m0[k & 3], v[k]); m1[k & 3] = max_nan(m1[k & 3], v[k]); }
+            float mn = min_nan(min_nan(m0[0], m0[1]), min_nan(m0[2], m0[3]));
+            float mx = max_nan(max_nan(m1[0], m1[1]), max_nan(m1[2], m1[3]));
+            for (int o = 1; o < lanes_per_block; o <<= 1) {
+                mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            AffineParams p = affine_params(mn, mx, L);
+            gp.a = p.mn; gp.s = p.scale; gp.r = p.rcp;
+            if (grow < n_rows && (lane & (lanes_per_block - 1)) == 0) {
+                const int64_t b = grow / lanes_per_block;
+                scale_out[b] = p.scale;
+                zp_out[b] = p.mn;
+            }
+        }
+
+        uint32_t u[kRowElems];
+        // warp-uniform choice keeps the common path free of per-element branches
+        if (CONV == kConvA && __all_sync(0xffffffffu, gp.r != 0.0f)) {
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) u[k] = elem_code_bits<CONV, true>(v[k], gp, L, Q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) u[k] = elem_code_bits<CONV, false>(v[k], gp, L, Q);
+        }
+
+        if (grow < n_rows) {
+            if (BITS == 4 && PACK) {
+                uint4 o;
+                o.x = pack_nibbles8<CONV>(u + 0);  o.y = pack_nibbles8<CONV>(u + 8);
+                o.z = pack_nibbles8<CONV>(u + 16); o.w = pack_nibbles8<CONV>(u + 24);
+                if (early) o = make_uint4(0, 0, 0, 0);
+                __stcs(reinterpret_cast<uint4*>(q_out + grow * 16), o);
+            } else {
+                uint32_t w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = early ? 0u : pack_bytes4<CONV, BITS>(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+                uint4* dst = reinterpret_cast<uint4*>(q_out + grow * 32);
+                __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+                __stcs(dst + 1, make_uint4(w[4], w[5], w[6], w[7]));
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// 3. dim-0 quantize: thread owns 4 columns, walks down the rows
+// --------------------------------------------------------------------------
+template <typename T, int BITS, bool PACK, int CONV>
+__global__ void __launch_bounds__(128) quantize_dim0_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
+                                                            int rows_per_chunk, uint8_t* __restrict__ q_out,
+                                                            const float* __restrict__ scale, const float* __restrict__ zp,
+                                                            const float* __restrict__ ws) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= cols) return;
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    constexpr float Q = BITS == 8 ? 127.0f : 7.0f;
+    const bool early = (CONV != kConvA) && reinterpret_cast<const int*>(ws)[0] != 0;
+    ElemParams p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { p[j].s = scale[c + j]; p[j].a = zp[c + j]; p[j].r = (CONV == kConvA) ? ws[kWsHeaderFloats + c + j] : 0.f; }
+    const int64_t r0 = (int64_t)(gridDim.y - 1 - blockIdx.y) * rows_per_chunk;   // newest-in-L2 first
+    const int64_t r1 = min(rows, r0 + rows_per_chunk);
+    auto load4 = [&](int64_t r, float* f) {
+        if (sizeof(T) == 4) {
+            float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * cols + c));
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
+            uint2 v = __ldcs(reinterpret_cast<const uint2*>(x + r * cols + c));
+            const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = to_f32(e[j]);
+        }
+    };
+    auto emit = [&](int64_t r, const float* f) {
+        uint32_t u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = elem_code_bits<CONV>(f[j], p[j], L, Q);
+        uint32_t w = early ? 0u : pack_bytes4<CONV, BITS>(u[0], u[1], u[2], u[3]);
+        if (BITS == 4 && PACK) {
+            // bytes b0..b3 (each <= 15) -> (b0 | b1<<4) | (b2 | b3<<4) << 8
+            uint32_t t = w | (w >> 4);
+            uint16_t h = (uint16_t)((t & 0xFFu) | ((t >> 8) & 0xFF00u));
+            *reinterpret_cast<uint16_t*>(q_out + (r * cols + c) / 2) = h;
+        } else {
+            *reinterpret_cast<uint32_t*>(q_out + r * cols + c) = w;
+        }
+    };
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        float f[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) load4(r + k, f[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit(r + k, f[k]);
+    }
+    for (; r < r1; ++r) { float f[4]; load4(r, f); emit(r, f); }
+}
+
+// --------------------------------------------------------------------------
+// 4. generic fallbacks (tails, odd shapes, unaligned pointers)
+// --------------------------------------------------------------------------
+// One thread per PAIR of elements of the flat range [start, n); channel of
+// element i is 0 (nchan == 1) or i % nchan.
+template <typename T, int BITS, bool PACK, int CONV>
+__global__ void __launch_bounds__(256) quantize_generic_kernel(const T* __restrict__ x, int64_t start, int64_t n,
+                                                               int64_t nchan, uint8_t* __restrict__ q_out,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ zp,
+                                                               const float* __restrict__ ws) {
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    constexpr float Q = BITS == 8 ? 127.0f : 7.0f;
+    constexpr uint32_t off = (CONV == kConvBSym) ? (BITS == 8 ? 128u : 8u) : 0u;
+    const bool early = (CONV != kConvA) && reinterpret_cast<const int*>(ws)[0] != 0;
+    const int64_t i0 = start + 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    uint32_t code[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int64_t i = i0 + k;
+        if (i < n) {
+            const int64_t c = nchan == 1 ? 0 : i % nchan;
+            ElemParams p{zp[c], scale[c], (CONV == kConvA) ? ws[kWsHeaderFloats + c] : 0.f};
+            uint32_t u = elem_code_bits<CONV>(to_f32(x[i]), p, L, Q);
+            code[k] = early ? 0u : ((u - kMagicBits + off) & 0xFFu);
+        }
+    }
+    if (BITS == 4 && PACK) {
+        q_out[i0 >> 1] = (uint8_t)(code[0] | (code[1] << 4));   // odd tail: pad nibble 0
+    } else {
+        q_out[i0] = (uint8_t)code[0];
+        if (i0 + 1 < n) q_out[i0 + 1] = (uint8_t)code[1];
+    }
+}
+
+// Blockwise, any block size: one warp per quantization block (two passes, the
+// second one served by L1/L2).  PACK needs an even block.
+template <typename T, int BITS, bool PACK>
+__global__ void __launch_bounds__(256) quantize_block_generic_kernel(const T* __restrict__ x, int64_t nblocks,
+                                                                     int64_t block, uint8_t* __restrict__ q_out,
+                                                                     float* __restrict__ scale_out,
+                                                                     float* __restrict__ zp_out) {
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const T* xb = x + b * block;
+    float mn = to_f32(xb[0]), mx = mn;
+    for (int64_t i = lane; i < block; i += 32) { float f = to_f32(xb[i]); mn = min_nan(mn, f); mx = max_nan(mx, f); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    AffineParams p = affine_params(mn, mx, L);
+    if (lane == 0) { scale_out[b] = p.scale; zp_out[b] = p.mn; }
+    if (BITS == 4 && PACK) {
+        uint8_t* qb = q_out + b * (block / 2);
+        for (int64_t i = 2 * lane; i < block; i += 64) {
+            uint32_t lo = code_bits(affine_quotient(to_f32(xb[i]), p), L) & 0xFu;
+            uint32_t hi = code_bits(affine_quotient(to_f32(xb[i + 1]), p), L) & 0xFu;
+            qb[i >> 1] = (uint8_t)(lo | (hi << 4));
+        }
+    } else {
+        uint8_t* qb = q_out + b * block;
+        for (int64_t i = lane; i < block; i += 32) qb[i] = (uint8_t)(code_bits(affine_quotient(to_f32(xb[i]), p), L) & 0xFFu);
+    }
+}
+
+// --------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, size_t elem_bytes, const void* base,
+                       uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
+                       uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return QUANTA_EDRIVER;
+    (void)elem_bytes;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? QUANTA_OK : QUANTA_EDRIVER;
+}
+
+template <typename T> struct TmaType;
+template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmaType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
+template <> struct TmaType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+
+static int grid_for_tiles(int64_t n_tiles) {
+    int64_t g = (int64_t)kNumSMs * 2;
+    return (int)(n_tiles < g ? n_tiles : g);
+}
+
+template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE>
+static int launch_rows_tma(const T* x, int64_t n_rows, int lanes_per_block, uint8_t* q, float* scale, float* zp,
+                           const float* ws, cudaStream_t st) {
+    using RL = RowLayout<T>;
+    CUtensorMap tmap;
+    int rc = make_tensor_map_2d(&tmap, TmaType<T>::v, sizeof(T), x, kRowElems, (uint64_t)n_rows, RL::kRowBytes,
+                                kRowElems, kTileRows,
+                                sizeof(T) == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    auto kern = quantize_rows_tma_kernel<T, BITS, PACK, CONV, BLOCKWISE>;
+    const int smem = kStages * RL::kTileBytes + 1024;
+    static bool attr_set = false;      // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    kern<<<grid_for_tiles(n_tiles), kTmaThreads, smem, st>>>(tmap, n_rows, lanes_per_block, q, scale, zp, ws);
+    return cuda_status(cudaGetLastError());
+}
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// TENSOR / DIM0 body shared by conventions A and B.
+template <typename T, int BITS, bool PACK, int CONV>
+static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, uint8_t* q, float* scale, float* zp,
+                            float* ws, cudaStream_t st) {
+    const int64_t n = rows * cols;
+    if (mode == QUANTA_MODE_TENSOR) {
+        float* pmin = ws + kWsHeaderFloats + 64;
+        float* pmax = pmin + kMaxPartialCtas;
+        int64_t want = (n + 256 * 16 - 1) / (256 * 16);
+        int g = (int)(want < 1 ? 1 : (want > kMaxPartialCtas ? kMaxPartialCtas : want));
+        minmax_tensor_partial_kernel<T><<<g, 256, 0, st>>>(x, n, pmin, pmax);
+        minmax_tensor_finalize_kernel<CONV><<<1, 256, 0, st>>>(pmin, pmax, g, BITS, scale, zp, ws);
+        int64_t n_rows = aligned16(x) && aligned16(q) ? n / kRowElems : 0;
+        if (n_rows > 0) {
+            int rc = launch_rows_tma<T, BITS, PACK, CONV, false>(x, n_rows, 1, q, scale, zp, ws, st);
+            if (rc) return rc;
+        }
+        const int64_t start = n_rows * kRowElems;
+        if (start < n) {
+            int64_t pairs = (n - start + 1) / 2;
+            quantize_generic_kernel<T, BITS, PACK, CONV><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+                x, start, n, 1, q, scale, zp, ws);
+        }
+        return cuda_status(cudaGetLastError());
+    }
+    // DIM0
+    float* rcp = ws + kWsHeaderFloats;
+    float* pmin = rcp + cols;
+    int nchunks = (int)((rows + 63) / 64);
+    if (nchunks > kMaxDim0Chunks) nchunks = kMaxDim0Chunks;
+    if (nchunks < 1) nchunks = 1;
+    const int rpc = (int)((rows + nchunks - 1) / nchunks);
+    nchunks = (int)((rows + rpc - 1) / rpc);
+    float* pmax = pmin + (int64_t)nchunks * cols;
+    const bool fast = (cols % 4 == 0) && aligned16(x) && aligned16(q) && aligned16(ws);
+    if (CONV != kConvA) dim0_flag_init_kernel<<<1, 1, 0, st>>>(ws, 1);
+    if (fast) {
+        dim3 g((unsigned)((cols / 4 + 127) / 128), nchunks);
+        minmax_dim0_partial_kernel<T><<<g, 128, 0, st>>>(x, rows, cols, rpc, pmin, pmax);
+    } else {
+        dim3 g((unsigned)((cols + 127) / 128), nchunks);
+        minmax_dim0_partial_generic_kernel<T><<<g, 128, 0, st>>>(x, rows, cols, rpc, pmin, pmax);
+    }
+    minmax_dim0_finalize_kernel<CONV><<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(pmin, pmax, nchunks, cols, BITS,
+                                                                                    scale, zp, ws);
+    if (CONV != kConvA) dim0_earlyout_params_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(cols, scale, zp, ws);
+    if (fast) {
+        int qchunks = (int)((rows + 31) / 32);
+        if (qchunks > 1024) qchunks = 1024;
+        const int qrpc = (int)((rows + qchunks - 1) / qchunks);
+        qchunks = (int)((rows + qrpc - 1) / qrpc);
+        dim3 g((unsigned)((cols / 4 + 127) / 128), qchunks);
+        quantize_dim0_kernel<T, BITS, PACK, CONV><<<g, 128, 0, st>>>(x, rows, cols, qrpc, q, scale, zp, ws);
+    } else {
+        int64_t pairs = (n + 1) / 2;
+        quantize_generic_kernel<T, BITS, PACK, CONV><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+            x, 0, n, cols, q, scale, zp, ws);
+    }
+    return cuda_status(cudaGetLastError());
+}
+
+template <typename T, int BITS, bool PACK>
+static int quantize_affine_t(const T* x, int64_t rows, int64_t cols, int mode, int64_t block, uint8_t* q, float* scale,
+                             float* zp, float* ws, cudaStream_t st) {
+    const int64_t n = rows * cols;
+    if (mode == QUANTA_MODE_BLOCK) {
+        const int64_t nblocks = n / block;
+        if (block % kRowElems == 0 && is_pow2(block / kRowElems) && block <= 1024 && aligned16(x) && aligned16(q))
+            return launch_rows_tma<T, BITS, PACK, kConvA, true>(x, n / kRowElems, (int)(block / kRowElems), q, scale, zp,
+                                                                ws, st);
+        if (PACK && (block & 1)) return QUANTA_EUNSUPPORTED;
+        quantize_block_generic_kernel<T, BITS, PACK><<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(x, nblocks, block, q,
+                                                                                                  scale, zp);
+        return cuda_status(cudaGetLastError());
+    }
+    return quantize_reduced<T, BITS, PACK, kConvA>(x, rows, cols, mode, q, scale, zp, ws, st);
+}
+
+template <typename T>
+static int quantize_affine_bits(const T* x, int64_t rows, int64_t cols, int mode, int64_t block, int bits, int pack,
+                                uint8_t* q, float* scale, float* zp, float* ws, cudaStream_t st) {
+    if (bits == 8) return quantize_affine_t<T, 8, false>(x, rows, cols, mode, block, q, scale, zp, ws, st);
+    if (pack) return quantize_affine_t<T, 4, true>(x, rows, cols, mode, block, q, scale, zp, ws, st);
+    return quantize_affine_t<T, 4, false>(x, rows, cols, mode, block, q, scale, zp, ws, st);
+}
+
+template <typename T>
+static int backend_quantize_t(const T* x, int64_t rows, int64_t cols, int per_channel, int symmetric, int bits,
+                              uint8_t* q, float* scale, float* zp, float* ws, cudaStream_t st) {
+    const int mode = per_channel ? QUANTA_MODE_DIM0 : QUANTA_MODE_TENSOR;
+    if (bits == 8) {
+        return symmetric ? quantize_reduced<T, 8, false, kConvBSym>(x, rows, cols, mode, q, scale, zp, ws, st)
+                         : quantize_reduced<T, 8, false, kConvBAsym>(x, rows, cols, mode, q, scale, zp, ws, st);
+    }
+    return symmetric ? quantize_reduced<T, 4, false, kConvBSym>(x, rows, cols, mode, q, scale, zp, ws, st)
+                     : quantize_reduced<T, 4, false, kConvBAsym>(x, rows, cols, mode, q, scale, zp, ws, st);
+}
+
+size_t quantize_workspace_bytes(int64_t cols) {
+    size_t tensor_part = (size_t)(kWsHeaderFloats + 64 + 2 * kMaxPartialCtas) * 4;
+    size_t dim0_part = (size_t)(kWsHeaderFloats + (int64_t)(2 * kMaxDim0Chunks + 1) * (cols < 1 ? 1 : cols)) * 4;
+    return (tensor_part > dim0_part ? tensor_part : dim0_part) + 256;
+}
+
+}  // namespace quanta
+
+using namespace quanta;
+
+extern "C" int quanta_quantize_affine(const void* x, int x_dtype, int64_t rows, int64_t cols, int mode, int64_t block,
+                                      int bits, int pack4, uint8_t* q_out, float* scale_out, float* zp_out,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !q_out || !scale_out || !zp_out) return QUANTA_EINVAL;
+    if (rows <= 0 || cols <= 0 || (bits != 8 && bits != 4) || (pack4 && bits != 4)) return QUANTA_EINVAL;
+    if (mode < QUANTA_MODE_TENSOR || mode > QUANTA_MODE_BLOCK) return QUANTA_EINVAL;
+    if (mode == QUANTA_MODE_BLOCK && (block <= 0 || (rows * cols) % block != 0)) return QUANTA_EINVAL;
+    if (mode != QUANTA_MODE_BLOCK) {
+        if (!workspace) return QUANTA_EINVAL;
+        if (workspace_bytes < quantize_workspace_bytes(mode == QUANTA_MODE_DIM0 ? cols : 1)) return QUANTA_EWORKSPACE;
+    }
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (x_dtype) {
+        case QUANTA_F32:
+            return quantize_affine_bits(static_cast<const float*>(x), rows, cols, mode, block, bits, pack4, q_out,
+                                        scale_out, zp_out, ws, st);
+        case QUANTA_F16:
+            return quantize_affine_bits(static_cast<const __half*>(x), rows, cols, mode, block, bits, pack4, q_out,
+                                        scale_out, zp_out, ws, st);
+        case QUANTA_BF16:
+            return quantize_affine_bits(static_cast<const __nv_bfloat16*>(x), rows, cols, mode, block, bits, pack4,
+                                        q_out, scale_out, zp_out, ws, st);
+    }
+    return QUANTA_EINVAL;
+}
+
+extern "C" int quanta_backend_quantize(const void* x, int x_dtype, int64_t rows, int64_t cols, int per_channel,
+                                       int symmetric, int bits, uint8_t* q_out, float* scale_out, float* zp_out,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !q_out || !scale_out || !zp_out || !workspace) return QUANTA_EINVAL;
+    if (rows <= 0 || cols <= 0 || (bits != 8 && bits != 4)) return QUANTA_EINVAL;
+    if (workspace_bytes < quantize_workspace_bytes(per_channel ? cols : 1)) return QUANTA_EWORKSPACE;
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (x_dtype) {
+        case QUANTA_F32:
+            return backend_quantize_t(static_cast<const float*>(x), rows, cols, per_channel, symmetric, bits, q_out,
+                                      scale_out, zp_out, ws, st);
+        case QUANTA_F16:
+            return backend_quantize_t(static_cast<const __half*>(x), rows, cols, per_channel, symmetric, bits, q_out,
+                                      scale_out, zp_out, ws, st);
+        case QUANTA_BF16:
+            return backend_quantize_t(static_cast<const __nv_bfloat16*>(x), rows, cols, per_channel, symmetric, bits,
+                                      q_out, scale_out, zp_out, ws, st);
+    }
+    return QUANTA_EINVAL;
+}

@@ -1,0 +1,5 @@
+"""Mirror of ``Quanta.functional`` (Quanta/functional/__init__.py:5-16 exports
+only the quantization primitives)."""
+from .quantization import quantize_8bit, quantize_4bit, dequantize_8bit, dequantize_4bit
+
+__all__ = ["quantize_8bit", "quantize_4bit", "dequantize_8bit", "dequantize_4bit"]

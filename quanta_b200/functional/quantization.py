@@ -1,0 +1,166 @@
+"""Drop-in CUDA implementation of ``Quanta.functional.quantization`` ("linear").
+
+Same names, argument meaning, return layout and error behaviour as the
+reference (Quanta/functional/quantization.py:7-71), computed by the sm_100a
+kernels behind include/quanta_b200.h:
+
+    q_tensor, scale, zero_point = quantize_8bit(tensor)              # :20
+    q_tensor, scale, zero_point = quantize_4bit(tensor, per_channel=True)
+    x = dequantize_8bit(q_tensor, scale, zero_point)                 # :33
+
+New keyword arguments default to the reference behaviour:
+  blocksize=B  blockwise quantization — the reference's ``per_channel=True``
+               branch applied to ``tensor.reshape(-1, B).t()`` (SURVEY Appendix
+               A.1); ``scale`` / ``zero_point`` come back with shape [numel/B],
+               codes keep the input's shape and order.
+  packed=True  (4-bit) codes are returned nibble-packed as
+               ``pack_4bit_tensor`` would (flat uint8 of ceil(numel/2)).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _host, _lib
+
+_NOT_BUILT = ("nf4", "fp4", "nf8", "fp8")
+
+
+def _quantize_linear(tensor, bits, per_channel, blocksize, packed):
+    _host.require_cuda(tensor)
+    x = tensor.detach()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    code = _host.dtype_code(x)
+    n = x.numel()
+    if n == 0:
+        raise RuntimeError("min(): cannot quantize an empty tensor")          # torch.min raises on empty input
+    dev = x.device
+    if blocksize is not None:
+        B = int(blocksize)
+        if B <= 0 or n % B:
+            raise ValueError(f"numel ({n}) must be a multiple of blocksize ({blocksize})")
+        mode, rows, cols, nparam, pshape = _lib.MODE_BLOCK, 1, n, n // B, (n // B,)
+    elif per_channel:
+        if x.dim() < 2:
+            # the reference calls tensor.min(dim=None, keepdim=True) here, which raises
+            raise ValueError("per_channel=True needs a tensor with dim() > 1")
+        rows, cols = _host.rows_cols(x)
+        mode, nparam, pshape, B = _lib.MODE_DIM0, cols, (1,) + tuple(x.shape[1:]), 0
+    else:
+        mode, rows, cols, nparam, pshape, B = _lib.MODE_TENSOR, 1, n, 1, (), 0
+    with torch.cuda.device(dev):
+        scale = torch.empty(nparam, dtype=torch.float32, device=dev)
+        zp = torch.empty(nparam, dtype=torch.float32, device=dev)
+        q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
+        ws_bytes = _lib.lib().quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, rows, cols)
+        ws = _host.workspace(dev, ws_bytes)
+        st = _lib.lib().quanta_quantize_affine(x.data_ptr(), code, rows, cols, mode, B, bits, int(bool(packed)),
+                                               q.data_ptr(), scale.data_ptr(), zp.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
+        if st == -2 and packed:
+            # odd block sizes: quantize unpacked, then pack (same bytes)
+            q = torch.empty(n, dtype=torch.uint8, device=dev)
+            st = _lib.lib().quanta_quantize_affine(x.data_ptr(), code, rows, cols, mode, B, bits, 0,
+                                                   q.data_ptr(), scale.data_ptr(), zp.data_ptr(),
+                                                   ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
+            _lib.check(st, "quanta_quantize_affine")
+            from ..utils.utils import pack_4bit_tensor
+            q = pack_4bit_tensor(q)[0]
+        else:
+            _lib.check(st, "quanta_quantize_affine")
+    if not packed:
+        q = q.reshape(tensor.shape)
+    return q, scale.reshape(pshape), zp.reshape(pshape)
+
+
+def quantize_4bit(tensor, quant_type="linear", per_channel=False, blocksize=None, packed=False):
+    """Quantize a floating-point tensor to 4-bit precision (codes 0..15, one per
+    uint8 unless ``packed``).  Mirrors Quanta/functional/quantization.py:7-18."""
+    if quant_type == "linear":
+        return _quantize_linear(tensor, 4, per_channel, blocksize, packed)
+    if quant_type in _NOT_BUILT[:2]:
+        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N1/N4), not built yet")
+    raise ValueError(f"Unknown quantization type: {quant_type}")
+
+
+def quantize_8bit(tensor, quant_type="linear", per_channel=False, blocksize=None):
+    """Quantize a floating-point tensor to 8-bit precision.
+    Mirrors Quanta/functional/quantization.py:20-31."""
+    if quant_type == "linear":
+        return _quantize_linear(tensor, 8, per_channel, blocksize, False)
+    if quant_type in _NOT_BUILT[2:]:
+        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N4), not built yet")
+    raise ValueError(f"Unknown quantization type: {quant_type}")
+
+
+def _dequantize_linear(q_tensor, scale, zero_point, blocksize, packed, shape, out_dtype):
+    _host.require_cuda(q_tensor, "q_tensor")
+    dev = q_tensor.device
+    q = q_tensor.detach()
+    if q.dtype != torch.uint8:
+        q = q.to(torch.uint8)
+    if not q.is_contiguous():
+        q = q.contiguous()
+    scale = torch.as_tensor(scale, dtype=torch.float32, device=dev).contiguous()
+    zp = torch.as_tensor(zero_point, dtype=torch.float32, device=dev).contiguous()
+    if packed:
+        out_shape = torch.Size(shape) if shape is not None else torch.Size([q.numel() * 2])
+    else:
+        out_shape = q.shape
+    n = out_shape.numel()
+    if n == 0:
+        return torch.empty(out_shape, dtype=out_dtype, device=dev)
+    ns = scale.numel()
+    if zp.numel() != ns:
+        if zp.numel() == 1:
+            zp = zp.expand(ns).contiguous()
+        elif ns == 1:
+            scale = scale.expand(zp.numel()).contiguous()
+            ns = zp.numel()
+        else:
+            raise ValueError("scale and zero_point must have the same number of elements")
+    rows, cols = (out_shape[0], n // out_shape[0]) if len(out_shape) > 1 else (1, n)
+    trailing = tuple(out_shape[1:])
+    if blocksize is not None:
+        B = int(blocksize)
+        if B <= 0 or n % B or ns != n // B:
+            raise ValueError("scale/zero_point do not match blocksize")
+        mode = _lib.MODE_BLOCK
+    elif ns == 1:
+        mode, B = _lib.MODE_TENSOR, 0
+    elif len(out_shape) > 1 and tuple(scale.shape) in ((1,) + trailing, trailing):
+        # the reference just broadcasts ``q.float() * scale``: a per_channel scale [1, *shape[1:]]
+        mode, B = _lib.MODE_DIM0, 0
+    else:
+        raise ValueError(f"scale of shape {tuple(scale.shape)} does not broadcast like the reference's per-tensor / "
+                         f"per_channel results over codes of shape {tuple(out_shape)}; pass blocksize= for blockwise")
+    out = torch.empty(out_shape, dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().quanta_dequantize_affine(q.data_ptr(), int(bool(packed)), rows, cols, mode, B,
+                                                 scale.data_ptr(), zp.data_ptr(), out.data_ptr(),
+                                                 _host._DTYPE[out_dtype], _host.stream_ptr(dev))
+    _lib.check(st, "quanta_dequantize_affine")
+    return out
+
+
+def dequantize_8bit(q_tensor, scale_or_levels, zero_point_or_bias, quant_type="linear", blocksize=None,
+                    out_dtype=torch.float32):
+    """Dequantize an 8-bit tensor back to floating point:
+    ``q.float() * scale + zero_point`` (Quanta/functional/quantization.py:33-38)."""
+    if quant_type == "linear":
+        return _dequantize_linear(q_tensor, scale_or_levels, zero_point_or_bias, blocksize, False, None, out_dtype)
+    if quant_type in _NOT_BUILT[2:]:
+        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N4), not built yet")
+    raise ValueError(f"Unknown quantization type: {quant_type}")
+
+
+def dequantize_4bit(q_tensor, scale_or_levels, zero_point_or_bias, quant_type="linear", blocksize=None,
+                    packed=False, shape=None, out_dtype=torch.float32):
+    """Dequantize a 4-bit tensor back to floating point
+    (Quanta/functional/quantization.py:53-58).  ``packed=True`` takes the
+    nibble-packed bytes of ``pack_4bit_tensor`` plus the original ``shape``."""
+    if quant_type == "linear":
+        return _dequantize_linear(q_tensor, scale_or_levels, zero_point_or_bias, blocksize, packed, shape, out_dtype)
+    if quant_type in _NOT_BUILT[:2]:
+        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N1/N4), not built yet")
+    raise ValueError(f"Unknown quantization type: {quant_type}")
