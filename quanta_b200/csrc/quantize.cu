@@ -11,6 +11,8 @@
 // common.cuh: affine_params / affine_quotient / code_bits).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace quanta {
 
 // --------------------------------------------------------------------------
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(128) minmax_dim0_partial_generic_kernel(const 
 __global__ void dim0_flag_init_kernel(float* ws, int value) { reinterpret_cast<int*>(ws)[0] = value; }
 
 template <int CONV>
-__global__ void __launch_bounds__(128) minmax_dim0_finalize_kernel(const float* __restrict__ pmin,
+__global__ void __launch_bounds__(32) minmax_dim0_finalize_kernel(const float* __restrict__ pmin,
                                                                    const float* __restrict__ pmax, int nchunks,
                                                                    int64_t cols, int bits, float* scale_out,
                                                                    float* zp_out, float* ws) {
@@ -254,7 +256,15 @@ __global__ void __launch_bounds__(128) minmax_dim0_finalize_kernel(const float* 
     bool close = true;
     if (c < cols) {
         float mn = pmin[c], mx = pmax[c];
-        for (int k = 1; k < nchunks; ++k) { mn = min_nan(mn, pmin[k * cols + c]); mx = max_nan(mx, pmax[k * cols + c]); }
+        int k = 1;
+        for (; k + 7 < nchunks; k += 8) {                 // 16 independent loads in flight
+            float a[8], b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = pmin[(int64_t)(k + j) * cols + c]; b[j] = pmax[(int64_t)(k + j) * cols + c]; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { mn = min_nan(mn, a[j]); mx = max_nan(mx, b[j]); }
+        }
+        for (; k < nchunks; ++k) { mn = min_nan(mn, pmin[(int64_t)k * cols + c]); mx = max_nan(mx, pmax[(int64_t)k * cols + c]); }
         float s, z, r;
         group_params<CONV>(mn, mx, bits, &s, &z, &r, &close);
         scale_out[c] = s; zp_out[c] = z;
@@ -292,22 +302,86 @@ template <typename T> struct RowLayout {
     }
 };
 
-template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE>
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0,
+                                                 int32_t c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
+// Cluster launch control (Blackwell work stealing): ask the hardware to cancel a
+// not-yet-launched CTA of this grid; the 16-byte response lands in shared memory
+// and completes `bar`.  Returns the cancelled CTA's blockIdx.x or -1.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_addr, uint32_t bar_addr) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 ::"r"(resp_addr), "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ int clc_read(uint32_t resp_addr) {
+    uint32_t valid, x;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p1;\n\t"
+        ".reg .b128 r;\n\t"
+        ".reg .b32 y, z;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+        "selp.u32 %1, 1, 0, p1;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, y, z, _}, r;\n\t"
+        "}\n"
+        : "=r"(x), "=r"(valid) : "r"(resp_addr) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    return valid ? (int)x : -1;
+}
+
+// a / L for L in {15, 255} with the reciprocal hoisted to a constant: exact for
+// every float in [2^-100, 2^100] (checked exhaustively on CPU, all 1.68e9 values).
+template <int BITS>
+__device__ __forceinline__ float div_by_levels(float a) {
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    constexpr float y = BITS == 8 ? 0.00392156862745098f : 0.06666666666666667f;   // RN(1/L)
+    float q0 = __fmul_rn(a, y);
+    float r = __fmaf_rn(-L, q0, a);
+    return __fmaf_rn(y, r, q0);
+}
+
+// Rare path (non-finite data, ranges outside [2^-50, 2^50]): generic IEEE
+// arithmetic, kept out of line so the hot loop stays small in the I-cache.
+template <int BITS>
+__device__ __noinline__ float slow_row_codes(const float* v, float mn, float mx, uint32_t* u) {
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    AffineParams p = affine_params(mn, mx, L);
+#pragma unroll 1
+    for (int k = 0; k < kRowElems; ++k) u[k] = code_bits(affine_quotient(v[k], p), L);
+    return p.scale;
+}
+
+template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE, bool DYN>
 __global__ void __launch_bounds__(kTmaThreads, 2)
-quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_rows, int lanes_per_block,
+quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_rows, int log2_lanes_per_block,
                          uint8_t* __restrict__ q_out, float* __restrict__ scale_out, float* __restrict__ zp_out,
-                         const float* __restrict__ ws) {
+                         const float* ws, int nparts) {
     using RL = RowLayout<T>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], clc_bar;
+    __shared__ __align__(16) uint4 clc_resp;
+    __shared__ int tile_of_stage[kStages];
 
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms are 1 KB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    const int n_tiles = (int)((n_rows + kTileRows - 1) / kTileRows);
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
+        mbar_init(&clc_bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -317,14 +391,27 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
         if (lane == 0) {
             prefetch_tensormap(&tmap);
             const uint64_t policy = policy_evict_first();
-            int i = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            int cta = blockIdx.x;          // DYN: this CTA's own tile first, then stolen ones
+            uint32_t clc_phase = 0;
+            for (int i = 0;; ++i) {
                 const int s = i % kStages;
                 const uint32_t ph = (i / kStages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
+                const bool live = cta >= 0 && cta < n_tiles;
+                const int t = !live ? -1 : (BLOCKWISE ? cta : n_tiles - 1 - cta);   // TENSOR pass 2: newest-in-L2 first
+                tile_of_stage[s] = t;
+                if (!live) { mbar_arrive(&full_bar[s]); break; }
                 mbar_arrive_expect_tx(&full_bar[s], RL::kTileBytes);
-                const int64_t tt = BLOCKWISE ? t : n_tiles - 1 - t;   // 2nd pass: newest-in-L2 first
-                tma_load_2d(smem + s * RL::kTileBytes, &tmap, &full_bar[s], 0, (int32_t)(tt * kTileRows), policy);
+                tma_load_2d_addr(smem + s * RL::kTileBytes, &tmap, smem_u32(&full_bar[s]), 0, t * kTileRows, policy);
+                if (DYN) {
+                    mbar_arrive_expect_tx(&clc_bar, 16);
+                    clc_try_cancel(smem_u32(&clc_resp), smem_u32(&clc_bar));
+                    mbar_wait(&clc_bar, clc_phase);
+                    clc_phase ^= 1;
+                    cta = clc_read(smem_u32(&clc_resp));
+                } else {
+                    cta += gridDim.x;
+                }
             }
         }
         return;
@@ -335,24 +422,49 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
     constexpr float Q = BITS == 8 ? 127.0f : 7.0f;
     ElemParams gp{0.f, 1.f, 0.f};
     bool early = false;
-    if (!BLOCKWISE) {   // TENSOR mode: parameters were produced by the finalize kernel
-        gp.s = scale_out[0];
-        gp.a = zp_out[0];
-        gp.r = ws[kWsHeaderFloats];
-        early = (CONV != kConvA) && reinterpret_cast<const int*>(ws)[0] != 0;
+    if (!BLOCKWISE) {
+        // TENSOR mode: every CTA reduces the per-CTA partial min/max of pass 1 itself
+        // (a few KB from L2) instead of waiting for a separate single-CTA finalize launch.
+        __shared__ float red_mn[kConsumerWarps], red_mx[kConsumerWarps];
+        const float* pmin = ws + kWsHeaderFloats + 64;
+        const float* pmax = pmin + kMaxPartialCtas;
+        float mn = pmin[0], mx = pmax[0];
+        for (int k = tid; k < nparts; k += kTileRows) { mn = min_nan(mn, pmin[k]); mx = max_nan(mx, pmax[k]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { red_mn[warp] = mn; red_mx[warp] = mx; }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTileRows) : "memory");      // consumers only
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) { mn = min_nan(mn, red_mn[w]); mx = max_nan(mx, red_mx[w]); }
+        float sc, z, r; bool close;
+        group_params<CONV>(mn, mx, BITS, &sc, &z, &r, &close);
+        early = (CONV != kConvA) && close;
+        if (early) { sc = 1.0f; z = mn; }                 // cpu/quantization.py:38-39
+        gp.s = sc; gp.a = z; gp.r = r;
+        if (blockIdx.x == 0 && tid == 0) {                // publish for the caller and the tail kernel
+            scale_out[0] = sc; zp_out[0] = z;
+            const_cast<float*>(ws)[kWsHeaderFloats] = r;
+            reinterpret_cast<int*>(const_cast<float*>(ws))[0] = early ? 1 : 0;
+        }
     }
+    const int lpb_mask = (1 << log2_lanes_per_block) - 1;
+    const uint32_t row_off = tid * RL::kRowBytes;
 
-    int i = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
+        const int t = *reinterpret_cast<volatile int*>(&tile_of_stage[s]);
+        if (t < 0) break;
 
         float v[kRowElems];
-        const uint8_t* row = smem + s * RL::kTileBytes + tid * RL::kRowBytes;
+        const uint32_t row = smem + s * RL::kTileBytes + row_off;
 #pragma unroll
         for (int j = 0; j < RL::kChunks; ++j) {
-            uint4 c = *reinterpret_cast<const uint4*>(row + (RL::swz(tid, j) << 4));
+            uint4 c = lds128(row + (RL::swz(tid, j) << 4));
             if (sizeof(T) == 4) {
                 v[4 * j + 0] = __uint_as_float(c.x); v[4 * j + 1] = __uint_as_float(c.y);
                 v[4 * j + 2] = __uint_as_float(c.z); v[4 * j + 3] = __uint_as_float(c.w);
@@ -365,7 +477,10 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);     // stage can be refilled while we compute
 
-        const int64_t grow = (BLOCKWISE ? t : n_tiles - 1 - t) * kTileRows + tid;      // global row
+        const int64_t grow = (int64_t)t * kTileRows + tid;      // global row
+        const bool row_ok = grow < n_rows;
+        uint32_t u[kRowElems];
+
         if (BLOCKWISE) {
             float m0[4], m1[4];
 #pragma unroll
@@ -374,30 +489,59 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
             for (int k = 4; k < kRowElems; ++k) { m0[k & 3] = min_nan(m0[k & 3], v[k]); m1[k & 3] = max_nan(m1[k & 3], v[k]); }
             float mn = min_nan(min_nan(m0[0], m0[1]), min_nan(m0[2], m0[3]));
             float mx = max_nan(max_nan(m1[0], m1[1]), max_nan(m1[2], m1[3]));
-            for (int o = 1; o < lanes_per_block; o <<= 1) {
+            for (int o = 1; o <= lpb_mask; o <<= 1) {
                 mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             }
-            AffineParams p = affine_params(mn, mx, L);
-            gp.a = p.mn; gp.s = p.scale; gp.r = p.rcp;
-            if (grow < n_rows && (lane & (lanes_per_block - 1)) == 0) {
-                const int64_t b = grow / lanes_per_block;
-                scale_out[b] = p.scale;
-                zp_out[b] = p.mn;
-            }
-        }
-
-        uint32_t u[kRowElems];
-        // warp-uniform choice keeps the common path free of per-element branches
-        if (CONV == kConvA && __all_sync(0xffffffffu, gp.r != 0.0f)) {
+            // quantization.py:195-196 / :205: degenerate range rule, scale = range / L
+            const float mx2 = (mx == mn) ? __fadd_rn(mn, 1e-6f) : mx;
+            const float range = __fsub_rn(mx2, mn);
+            // range in [2^-50, 2^50] (false for NaN/inf): constant-reciprocal divide and
+            // hoisted-reciprocal quotients are exact, and x in [mn, mx] makes the clamp a no-op
+            const bool fast = range >= 8.881784197001252e-16f && range <= 1125899906842624.0f;
+            float scale;
+            if (__all_sync(0xffffffffu, fast)) {
+                scale = div_by_levels<BITS>(range);
+                const float rcp = __frcp_rn(scale);
+                const float nscale = -scale;
 #pragma unroll
-            for (int k = 0; k < kRowElems; ++k) u[k] = elem_code_bits<CONV, true>(v[k], gp, L, Q);
+                for (int k = 0; k < kRowElems; ++k) {
+                    const float a = __fsub_rn(v[k], mn);
+                    const float q0 = __fmul_rn(a, rcp);
+                    const float r = __fmaf_rn(nscale, q0, a);
+                    u[k] = __float_as_uint(__fadd_rn(__fmaf_rn(rcp, r, q0), kMagic));
+                }
+            } else {
+                // copies keep v[] / u[] in registers on the hot path (only these temporaries live on the stack)
+                float vs[kRowElems];
+                uint32_t us[kRowElems];
+#pragma unroll
+                for (int k = 0; k < kRowElems; ++k) vs[k] = v[k];
+                scale = slow_row_codes<BITS>(vs, mn, mx, us);
+#pragma unroll
+                for (int k = 0; k < kRowElems; ++k) u[k] = us[k];
+            }
+            if (row_ok && (lane & lpb_mask) == 0) {
+                const int64_t b = grow >> log2_lanes_per_block;
+                scale_out[b] = scale;
+                zp_out[b] = mn;
+            }
+        } else if (CONV == kConvA && gp.r != 0.0f) {
+            const float nscale = -gp.s;
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) {
+                const float a = __fsub_rn(v[k], gp.a);
+                const float q0 = __fmul_rn(a, gp.r);
+                const float r = __fmaf_rn(nscale, q0, a);
+                // rows past the end of the tensor are zero-filled by TMA: clamp keeps them harmless
+                u[k] = code_bits(__fmaf_rn(gp.r, r, q0), L);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < kRowElems; ++k) u[k] = elem_code_bits<CONV, false>(v[k], gp, L, Q);
         }
 
-        if (grow < n_rows) {
+        if (row_ok) {
             if (BITS == 4 && PACK) {
                 uint4 o;
                 o.x = pack_nibbles8<CONV>(u + 0);  o.y = pack_nibbles8<CONV>(u + 8);
@@ -580,16 +724,25 @@ static int grid_for_tiles(int64_t n_tiles) {
     return (int)(n_tiles < g ? n_tiles : g);
 }
 
-template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE>
-static int launch_rows_tma(const T* x, int64_t n_rows, int lanes_per_block, uint8_t* q, float* scale, float* zp,
-                           const float* ws, cudaStream_t st) {
+static bool use_clc() {
+    static const bool v = []() {
+        const char* e = getenv("QUANTA_B200_STATIC_TILES");      // escape hatch: static round-robin tiles
+        return !(e && e[0] == '1');
+    }();
+    return v;
+}
+
+static int log2_of(int64_t v) {
+    int s = 0;
+    while ((int64_t(1) << s) < v) ++s;
+    return s;
+}
+
+template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE, bool DYN>
+static int launch_rows_tma_impl(const CUtensorMap& tmap, int64_t n_rows, int lanes_per_block, uint8_t* q, float* scale,
+                                float* zp, const float* ws, int nparts, cudaStream_t st) {
     using RL = RowLayout<T>;
-    CUtensorMap tmap;
-    int rc = make_tensor_map_2d(&tmap, TmaType<T>::v, sizeof(T), x, kRowElems, (uint64_t)n_rows, RL::kRowBytes,
-                                kRowElems, kTileRows,
-                                sizeof(T) == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-    auto kern = quantize_rows_tma_kernel<T, BITS, PACK, CONV, BLOCKWISE>;
+    auto kern = quantize_rows_tma_kernel<T, BITS, PACK, CONV, BLOCKWISE, DYN>;
     const int smem = kStages * RL::kTileBytes + 1024;
     static bool attr_set = false;      // per instantiation
     if (!attr_set) {
@@ -598,8 +751,24 @@ static int launch_rows_tma(const T* x, int64_t n_rows, int lanes_per_block, uint
         attr_set = true;
     }
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
-    kern<<<grid_for_tiles(n_tiles), kTmaThreads, smem, st>>>(tmap, n_rows, lanes_per_block, q, scale, zp, ws);
+    // DYN: one CTA per tile; resident CTAs steal the not-yet-launched ones (cluster launch control)
+    const unsigned grid = DYN ? (unsigned)n_tiles : (unsigned)grid_for_tiles(n_tiles);
+    kern<<<grid, kTmaThreads, smem, st>>>(tmap, n_rows, log2_of(lanes_per_block), q, scale, zp, ws, nparts);
     return cuda_status(cudaGetLastError());
+}
+
+template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE>
+static int launch_rows_tma(const T* x, int64_t n_rows, int lanes_per_block, uint8_t* q, float* scale, float* zp,
+                           const float* ws, int nparts, cudaStream_t st) {
+    using RL = RowLayout<T>;
+    CUtensorMap tmap;
+    int rc = make_tensor_map_2d(&tmap, TmaType<T>::v, sizeof(T), x, kRowElems, (uint64_t)n_rows, RL::kRowBytes,
+                                kRowElems, kTileRows,
+                                sizeof(T) == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (use_clc())
+        return launch_rows_tma_impl<T, BITS, PACK, CONV, BLOCKWISE, true>(tmap, n_rows, lanes_per_block, q, scale, zp, ws, nparts, st);
+    return launch_rows_tma_impl<T, BITS, PACK, CONV, BLOCKWISE, false>(tmap, n_rows, lanes_per_block, q, scale, zp, ws, nparts, st);
 }
 
 static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -614,13 +783,16 @@ static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, ui
         float* pmin = ws + kWsHeaderFloats + 64;
         float* pmax = pmin + kMaxPartialCtas;
         int64_t want = (n + 256 * 16 - 1) / (256 * 16);
-        int g = (int)(want < 1 ? 1 : (want > kMaxPartialCtas ? kMaxPartialCtas : want));
+        const int cap = kNumSMs * 4;                       // 4 resident CTAs of 256 threads per SM
+        int g = (int)(want < 1 ? 1 : (want > cap ? cap : want));
         minmax_tensor_partial_kernel<T><<<g, 256, 0, st>>>(x, n, pmin, pmax);
-        minmax_tensor_finalize_kernel<CONV><<<1, 256, 0, st>>>(pmin, pmax, g, BITS, scale, zp, ws);
         int64_t n_rows = aligned16(x) && aligned16(q) ? n / kRowElems : 0;
         if (n_rows > 0) {
-            int rc = launch_rows_tma<T, BITS, PACK, CONV, false>(x, n_rows, 1, q, scale, zp, ws, st);
+            // the streaming kernel finalizes the reduction itself and publishes scale / zp
+            int rc = launch_rows_tma<T, BITS, PACK, CONV, false>(x, n_rows, 1, q, scale, zp, ws, g, st);
             if (rc) return rc;
+        } else {
+            minmax_tensor_finalize_kernel<CONV><<<1, 256, 0, st>>>(pmin, pmax, g, BITS, scale, zp, ws);
         }
         const int64_t start = n_rows * kRowElems;
         if (start < n) {
@@ -648,8 +820,8 @@ static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, ui
         dim3 g((unsigned)((cols + 127) / 128), nchunks);
         minmax_dim0_partial_generic_kernel<T><<<g, 128, 0, st>>>(x, rows, cols, rpc, pmin, pmax);
     }
-    minmax_dim0_finalize_kernel<CONV><<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(pmin, pmax, nchunks, cols, BITS,
-                                                                                    scale, zp, ws);
+    minmax_dim0_finalize_kernel<CONV><<<(unsigned)((cols + 31) / 32), 32, 0, st>>>(pmin, pmax, nchunks, cols, BITS,
+                                                                                  scale, zp, ws);
     if (CONV != kConvA) dim0_earlyout_params_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(cols, scale, zp, ws);
     if (fast) {
         int qchunks = (int)((rows + 31) / 32);
@@ -674,7 +846,7 @@ static int quantize_affine_t(const T* x, int64_t rows, int64_t cols, int mode, i
         const int64_t nblocks = n / block;
         if (block % kRowElems == 0 && is_pow2(block / kRowElems) && block <= 1024 && aligned16(x) && aligned16(q))
             return launch_rows_tma<T, BITS, PACK, kConvA, true>(x, n / kRowElems, (int)(block / kRowElems), q, scale, zp,
-                                                                ws, st);
+                                                                ws, 0, st);
         if (PACK && (block & 1)) return QUANTA_EUNSUPPORTED;
         quantize_block_generic_kernel<T, BITS, PACK><<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(x, nblocks, block, q,
                                                                                                   scale, zp);

@@ -82,3 +82,11 @@ def test_error_behaviour_mirrors_reference():
         Q.dequantize_4bit(x, x, x, quant_type="bogus")
     with pytest.raises(ValueError, match="Input tensor must be uint8"):        # utils/utils.py:25-26
         Q.pack_4bit_tensor(torch.zeros(4, dtype=torch.int32))
+
+
+def test_workspace_sizes_are_small():
+    """Per-tensor mode needs a few KB; dim-0 mode scales with the column count only."""
+    h = _lib.lib()
+    assert h.quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, 1, 1) < (1 << 16)
+    assert h.quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, 11008, 4096) < (4 << 20)
+    assert h.quanta_workspace_bytes(_lib.OP_BACKEND_DEQUANTIZE, 4096, 4096) == 256
