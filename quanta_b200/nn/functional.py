@@ -1,0 +1,43 @@
+"""Host wrappers of the fused dequantize-then-matmul entry points."""
+from __future__ import annotations
+
+import torch
+
+from .. import _host, _lib
+
+
+def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features=None, in_features=None):
+    """y = x @ dequant(Wq).T + bias on the tcgen05 tensor cores.
+
+    x      [..., K]   float16 / bfloat16 (CUDA)
+    wq     bits=8: uint8 [N, K];  bits=4: nibble-packed uint8 [N*K/2] or [N, K/2]
+           (``pack_4bit_tensor`` layout: even k -> low nibble)
+    scale, zp  float32 [N*K/blocksize] — convention A, blockwise along K
+           (``quantize_*bit(w, blocksize=B)``), blocksize = 64 * 2^j
+    """
+    _host.require_cuda(x, "x")
+    if x.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("x must be float16 or bfloat16")
+    K = x.shape[-1]
+    if in_features is not None and in_features != K:
+        raise ValueError(f"x has {K} features, layer expects {in_features}")
+    N = out_features if out_features is not None else (wq.shape[0] if wq.dim() == 2 else None)
+    if N is None:
+        raise ValueError("out_features is required for flat packed weights")
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    dev = x.device
+    y = torch.empty((M, N), dtype=x.dtype, device=dev)
+    if M == 0:
+        return y.reshape(*x.shape[:-1], N)
+    if bias is not None:
+        bias = bias.to(device=dev, dtype=x.dtype).contiguous()
+    with torch.cuda.device(dev):
+        ws = _host.workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+        st = _lib.lib().quanta_gemm_wna16(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits, scale.data_ptr(),
+                                          zp.data_ptr(), blocksize, bias.data_ptr() if bias is not None else None,
+                                          y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
+    _lib.check(st, "quanta_gemm_wna16")
+    return y.reshape(*x.shape[:-1], N)

@@ -1,0 +1,107 @@
+"""GPU tests of the fused dequantize-then-matmul (rows G1/G2).  The oracle is
+the composition the reference's layers imply: F.linear(x, dequantize(q).to(x.dtype))
+evaluated in float64 on the CPU (oracle.linear_dequant).  Tolerance (north_star):
+1e-2 relative in bf16 — measured as max|y - ref| / max|ref|."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_c as OC
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def make_case(N, K, M, bits, dtype, seed, bias=True):
+    import quanta_b200 as Q
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(N, K, generator=g) * 0.02
+    x = torch.randn(M, K, generator=g).to(dtype)
+    b = (torch.randn(N, generator=g) * 0.1).to(dtype) if bias else None
+    wd = w.cuda()
+    if bits == 4:
+        q, s, z = Q.quantize_4bit(wd, blocksize=64, packed=True)
+    else:
+        q, s, z = Q.quantize_8bit(wd, blocksize=64)
+    return w, x, b, q, s, z
+
+
+def reference(x, q, s, z, b, bits, N, K, dtype):
+    """float64 composition oracle on the codes the GPU produced (codes themselves are
+    checked bit-exactly in test_gpu_quantize.py)."""
+    name = "bf16" if dtype == torch.bfloat16 else "fp16"
+    xf = x.float().numpy()
+    wq = q.cpu().numpy()
+    if name == "bf16":
+        return OC.linear_dequant(xf, wq, s.cpu().numpy(), z.cpu().numpy(), None if b is None else b.float().numpy(),
+                                 bits, N, K, 64)
+    codes = O.unpack4(wq)[: N * K].reshape(N, K) if bits == 4 else wq.reshape(N, K)
+    return O.linear_dequant(xf, codes, s.cpu().numpy(), z.cpu().numpy(), None if b is None else b.float().numpy(), 64, name)
+
+
+def rel_err(y, ref):
+    return float(np.abs(y - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(128, 64, 1), (128, 256, 16), (256, 512, 5), (384, 1024, 33), (1024, 4096, 64),
+                                   (200, 320, 7), (512, 2048, 256), (256, 1024, 300)])
+def test_gemm_matches_composition_oracle(bits, dtype, shape):
+    from quanta_b200.nn import linear_wna16
+    N, K, M = shape
+    w, x, b, q, s, z = make_case(N, K, M, bits, dtype, seed=N + K + M + bits)
+    y = linear_wna16(x.cuda(), q, s, z, b.cuda(), bits=bits, blocksize=64, out_features=N)
+    assert y.shape == (M, N) and y.dtype == dtype
+    ref = reference(x, q, s, z, b, bits, N, K, dtype)
+    err = rel_err(y.float().cpu().numpy(), ref)
+    assert err < TOL, f"rel err {err:.3e} for N={N} K={K} M={M} bits={bits} {dtype}"
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_gemm_llama3_8b_shapes(bits):
+    """Config 3: (N,K) in {(4096,14336),(14336,4096)}, M in 1..256 (subset), bf16."""
+    from quanta_b200.nn import linear_wna16
+    for (N, K) in ((4096, 14336), (14336, 4096)):
+        w, x, b, q, s, z = make_case(N, K, 256, bits, torch.bfloat16, seed=N + bits, bias=False)
+        xd = x.cuda()
+        for M in (1, 16, 64, 256):
+            y = linear_wna16(xd[:M], q, s, z, None, bits=bits, blocksize=64, out_features=N)
+            # oracle on a slice of output features to keep the CPU time bounded
+            cols = slice(0, 256)
+            nb = K // 64
+            ref = OC.linear_dequant(x[:M].float().numpy(),
+                                    q.cpu().numpy().reshape(N, -1)[cols], s.cpu().numpy().reshape(N, nb)[cols],
+                                    z.cpu().numpy().reshape(N, nb)[cols], None, bits, 256, K, 64)
+            err = rel_err(y[:, cols].float().cpu().numpy(), ref)
+            assert err < TOL, f"rel err {err:.3e} N={N} K={K} M={M} bits={bits}"
+            # full-size property: against torch matmul with the GPU-dequantized weight (same rounding to bf16)
+            from quanta_b200 import dequantize_4bit, dequantize_8bit
+            wd = (dequantize_4bit(q, s, z, blocksize=64, packed=True, shape=(N, K), out_dtype=torch.bfloat16) if bits == 4
+                  else dequantize_8bit(q.reshape(N, K), s, z, blocksize=64, out_dtype=torch.bfloat16))
+            yt = (xd[:M].float() @ wd.float().t())
+            e2 = float((y.float() - yt).abs().max() / yt.abs().max())
+            assert e2 < TOL, f"vs torch fp32 matmul: {e2:.3e}"
+
+
+def test_linear_modules_mirror_reference_api():
+    from quanta_b200.nn import Linear4bit, Linear8bitLt
+    torch.manual_seed(0)
+    l4 = Linear4bit(512, 256, bias=True, compute_dtype=torch.bfloat16, quant_type="linear").cuda()
+    l8 = Linear8bitLt(512, 256, bias=True, has_fp16_weights=False, threshold=6.0).cuda()
+    assert l4.in_features == 512 and l4.out_features == 256 and l4.compute_dtype == torch.bfloat16
+    assert l8.threshold == 6.0 and l8.has_fp16_weights is False
+    for lin, dt in ((l4, torch.bfloat16), (l8, torch.float16)):
+        w = lin.weight.detach().clone()
+        x = torch.randn(3, 7, 512, device="cuda", dtype=dt)
+        y = lin(x)
+        assert y.shape == (3, 7, 256) and y.dtype == dt
+        wd = lin.dequantize_weight(dt)
+        ref = torch.nn.functional.linear(x.float(), wd.float(), lin.bias.float())
+        assert float((y.float() - ref).abs().max() / ref.abs().max()) < TOL
+        # and close to the unquantized layer (quantization error only)
+        ref_fp = torch.nn.functional.linear(x.float(), w.float(), lin.bias.float())
+        assert float((y.float() - ref_fp).abs().max() / ref_fp.abs().max()) < (0.15 if lin.bits == 4 else 0.02)
+    with pytest.raises(NotImplementedError):
+        Linear4bit(64, 64).cuda()(torch.randn(1, 64, device="cuda", dtype=torch.float16))   # default quant_type="nf4"
