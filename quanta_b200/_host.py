@@ -39,6 +39,22 @@ def workspace(device, nbytes):
     return buf
 
 
+_gemm_workspaces = {}
+
+
+def gemm_workspace(device, nbytes):
+    """Per (device, stream) workspace of the dequant-GEMM.  Its head holds the
+    stream-K arrival counters, which must be zero before the first call and are
+    left zero by every call (include/quanta_b200.h), so this buffer is
+    zero-initialised once and never shared with the other kernels' scratch."""
+    key = (device.index, stream_ptr(device))
+    buf = _gemm_workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+        _gemm_workspaces[key] = buf
+    return buf
+
+
 def rows_cols(t):
     """[rows, cols] view of a contiguous tensor: dim 0 x everything else."""
     if t.dim() == 0:

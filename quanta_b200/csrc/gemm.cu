@@ -1,38 +1,49 @@
 // W4A16 / W8A16 dequantize-then-matmul on the 5th-generation tensor cores
 // (rows G1/G2 of SURVEY §8): y[M,N] = x[M,K] . dequant(Wq)[N,K]^T + bias.
 //
-// Mapping ("swap-AB"): the weight tile's 128 output features are the UMMA M
+// Mapping ("swap-AB"): the 128 output features of a weight tile are the UMMA M
 // dimension (one TMEM lane each), the batch rows are the UMMA N dimension
 // (16..256), so small batches do not waste the 128-row MMA:
-//     D[n, m] (fp32, TMEM) += A[n, k] (dequantized weights, smem) * B[m, k] (x, smem)
-// Per 64-wide K block and pipeline stage:
-//   warp 0      TMA: raw weight codes [128 x 64] (u8 or nibble-packed) and x [MB x 64]
-//               (SWIZZLE_128B) -> shared memory, completes tma_full[s]
-//   warps 2..5  dequantize: thread = weight row; codes -> act dtype with the block's
-//               scale / zero-point, written as the K-major SWIZZLE_128B A tile;
-//               fence.proxy.async; arrive a_full[s]
-//   warp 1      one lane issues 4 x tcgen05.mma (K = 16 each); tcgen05.commit frees the stage
-// After the last K block the four dequant warps read the accumulator with
-// tcgen05.ld (lane = output feature) and store y (or a split-K partial).
+//     D[n, m] (fp32, TMEM) += A[n, k] (dequantized weights, TMEM) * B[m, k] (x, smem)
+// The dequantized A operand never touches shared memory: the dequant warps write
+// it straight into tensor memory (tcgen05.st) and the MMA reads A from TMEM.
+//
+// Persistent, warp-specialised CTA (one per SM), 24 warps:
+//   warp 0      TMA ring of raw weight codes: stages of [128 rows x 128 B] (SWIZZLE_128B),
+//               i.e. 256 K values of 4-bit or 128 of 8-bit codes per box
+//   warp 1      TMA ring of activation tiles [mb x 64] (SWIZZLE_128B, K-major B operand)
+//   warp 2      TMEM allocation; one lane issues tcgen05.mma.kind::f16 (4 x K=16 per 64-K block)
+//   warps 4-7   epilogue: tcgen05.ld the accumulator, add bias, store y — or store an fp32
+//               partial and let the last-arriving CTA of the tile reduce all partials
+//   warps 8-23  dequantize: 2 groups x 8 warps; a group owns every other stage and its own half of
+//               the A slots and raw slots (so every mbarrier has one producer and one consumer
+//               side and parity waits are unambiguous); a thread owns half a 64-K block of one
+//               weight row (= its TMEM lane): 32 codes -> 16-bit A values -> one tcgen05.st
+// Work is split stream-K style: the (tile, K-stage) units are cut into G equal
+// contiguous ranges, one per CTA, so all SMs stream weights for the same time.
 #include "common.cuh"
 
+#include <cmath>
 #include <cstdlib>
+#include <cstdio>
 
 namespace quanta {
 
-constexpr int kDequantWarps = 8;      // warps that cooperate on one K block (each thread: half a weight row)
-constexpr int kDequantGroups = 2;     // groups work on alternating K blocks -> 4 dequant warps per scheduler
-constexpr int kFirstDequantWarp = 3;  // warp 0: raw-code TMA, warp 1: activation TMA, warp 2: MMA issuer + TMEM
-constexpr int kGemmThreads = 32 * (kFirstDequantWarp + kDequantWarps * kDequantGroups);
-constexpr int kMaxRawStages = 32;
-constexpr int kAStages = 4;           // dequantized A tiles in flight (even: the groups alternate)
-constexpr int kTileN = 128;          // output features per CTA (UMMA M)
-constexpr int kBlockK = 64;          // K elements per stage = one 128-byte swizzle atom of 16-bit values
-constexpr int kATileBytes = kTileN * kBlockK * 2;
+constexpr int kTileN = 128;          // output features per tile (UMMA M, TMEM lanes)
+constexpr int kBlockK = 64;          // K per A slot / MMA group: one 128-byte swizzle atom of 16-bit activations
+constexpr int kKbPerStage = 4;       // 64-K blocks per raw-code stage
+constexpr int kStageK = kBlockK * kKbPerStage;
+constexpr int kASlots = 8;           // dequantized A tiles resident in TMEM
+constexpr int kACols = kBlockK / 2;  // 32-bit TMEM columns per A slot (two 16-bit values per column)
+constexpr int kDBase = kASlots * kACols;   // accumulators start at TMEM column 256
+constexpr int kTmemCols = 512;
+constexpr int kCtrlWarps = 4, kEpiWarps = 4, kDqGroups = 2, kDqGroupWarps = 8, kDqWarps = kDqGroupWarps * kDqGroups;
+constexpr int kFirstEpiWarp = kCtrlWarps, kFirstDqWarp = kCtrlWarps + kEpiWarps;
+constexpr int kGemmThreads = 32 * (kCtrlWarps + kEpiWarps + kDqWarps);
+constexpr int kMaxRing = 12;
+constexpr int kCounterBytes = 64 * 1024;     // per-tile arrival counters at the head of the workspace
+constexpr int kMaxTiles = kCounterBytes / 4;
 
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ uint4 lds128g(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -40,6 +51,10 @@ __device__ __forceinline__ uint4 lds128g(uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t prmt_(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r;
+}
+// (a & b) | c in one LOP3
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
 __device__ __forceinline__ void tma_load_2d_plain(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0,
                                                   int32_t c1, uint64_t policy) {
@@ -60,24 +75,35 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // completes `bar` (one arrival) when all previously issued MMAs of this thread have finished
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row
 // swizzle atoms 1024 bytes apart (SBO), LBO unused, descriptor version 1 (sm_100).
@@ -90,9 +116,9 @@ template <typename ACT> struct ActTraits;
 template <> struct ActTraits<__nv_bfloat16> {
     static constexpr uint32_t kFmt = 1;                  // UMMA F16F32Format::BF16
     static constexpr uint32_t kMagic = 0x43004300u;      // bf16x2 (128 + n)
+    static constexpr float kCentre = 136.0f;             // 128 + 8
     static constexpr CUtensorMapDataType kTma = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     using V2 = __nv_bfloat162;
-    __device__ static __forceinline__ V2 bias2() { return __float2bfloat162_rn(128.0f); }
     __device__ static __forceinline__ V2 dup(float v) { return __float2bfloat162_rn(v); }
     __device__ static __forceinline__ uint32_t pack(float a, float b) {
         V2 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&t);
@@ -103,9 +129,9 @@ template <> struct ActTraits<__nv_bfloat16> {
 template <> struct ActTraits<__half> {
     static constexpr uint32_t kFmt = 0;                  // F16
     static constexpr uint32_t kMagic = 0x64006400u;      // fp16x2 (1024 + n)
+    static constexpr float kCentre = 1032.0f;            // 1024 + 8
     static constexpr CUtensorMapDataType kTma = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     using V2 = __half2;
-    __device__ static __forceinline__ V2 bias2() { return __float2half2_rn(1024.0f); }
     __device__ static __forceinline__ V2 dup(float v) { return __float2half2_rn(v); }
     __device__ static __forceinline__ uint32_t pack(float a, float b) {
         V2 t = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&t);
@@ -114,332 +140,555 @@ template <> struct ActTraits<__half> {
     __device__ static __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
 };
 
-// pack two fp32 values into the A operand's 16-bit format
-template <uint32_t kAFmt>
-__device__ __forceinline__ uint32_t pack_a(float a, float b) {
-    if (kAFmt == 0) { __half2 t = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
+// 4-bit: one 32-bit word = nibbles n0..n7 = 8 consecutive K values (pack_4bit_tensor layout).
+// (magic | nibble) is the 16-bit float 128+n (bf16) / 1024+n (fp16), exactly; subtracting the
+// centre leaves n-8 exactly, and one packed fma gives (n-8)*s + (z+8s) = n*s + z with the scale
+// and the block midpoint z+8s rounded to the activation type (the midpoint is near zero for
+// weight-like data, so its rounding error is far below the final 16-bit rounding of the weight).
+template <typename ACT>
+__device__ __forceinline__ void dequant_word4(uint32_t w, typename ActTraits<ACT>::V2 s2, typename ActTraits<ACT>::V2 z2,
+                                              typename ActTraits<ACT>::V2 c2, uint32_t* out) {
+    using V2 = typename ActTraits<ACT>::V2;
+    constexpr uint32_t kM = ActTraits<ACT>::kMagic;
+    uint32_t t[4];
+    t[0] = and_or(w, 0x000F000Fu, kM);             // (n0, n4)
+    t[1] = and_or(w >> 4, 0x000F000Fu, kM);        // (n1, n5)
+    t[2] = and_or(w >> 8, 0x000F000Fu, kM);        // (n2, n6)
+    t[3] = and_or(w >> 12, 0x000F000Fu, kM);       // (n3, n7)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        V2 v = *reinterpret_cast<V2*>(&t[i]);
+        v = __hfma2(__hsub2(v, c2), s2, z2);
+        t[i] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    out[0] = prmt_(t[0], t[1], 0x5410u);           // (k0, k1)
+    out[1] = prmt_(t[2], t[3], 0x5410u);           // (k2, k3)
+    out[2] = prmt_(t[0], t[1], 0x7632u);           // (k4, k5)
+    out[3] = prmt_(t[2], t[3], 0x7632u);           // (k6, k7)
 }
 
-// dequantize one packed pair register: ((magic | nibbles) - bias) * scale + zp in 16-bit x2 math
+// 8-bit: PRMT drops a code byte into bits 8..15 of 0x47000000, i.e. builds the fp32 value
+// 32768 + q exactly; fma with zc = z - 32768*s gives q*s + z to within 2^-9 of a scale step,
+// far inside the 16-bit rounding that follows (the reference rounds mul and add separately).
 template <typename ACT>
-__device__ __forceinline__ uint32_t dq_pair(uint32_t nib2, typename ActTraits<ACT>::V2 s2, typename ActTraits<ACT>::V2 z2) {
-    using V2 = typename ActTraits<ACT>::V2;
-    uint32_t m = nib2 | ActTraits<ACT>::kMagic;
-    V2 t = *reinterpret_cast<V2*>(&m);
-    t = __hsub2(t, ActTraits<ACT>::bias2());
-    t = __hfma2(t, s2, z2);
-    return *reinterpret_cast<uint32_t*>(&t);
+__device__ __forceinline__ void dequant_word8(uint32_t w, float s, float zc, uint32_t* out) {
+    float f[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        f[e] = __fmaf_rn(__uint_as_float(prmt_(w, 0x47000000u, 0x7504u | (e << 4))), s, zc);
+    out[0] = ActTraits<ACT>::pack(f[0], f[1]);
+    out[1] = ActTraits<ACT>::pack(f[2], f[3]);
 }
 
 struct GemmParams {
     int M, N, K;
-    int mb;                 // UMMA N: batch rows per CTA tile (multiple of 16, <= 256)
-    int split_k;            // number of K splits
-    int kblocks_per_split;  // 64-wide K blocks per split
-    int raw_stages;         // deep ring of raw weight codes: this is what keeps HBM busy
-    int x_stages;           // ring of activation tiles
+    int mb;                 // UMMA N: batch rows per tile (multiple of 16, <= 256)
+    int n_tiles, m_tiles;
+    int total_kb;           // K / 64
+    int S;                  // raw-code stages per tile: ceil(total_kb / 4)
+    int G;                  // CTAs
+    unsigned int U;         // work units: tiles * S  (U * G < 2^32, checked on the host)
+    int nbuf;               // accumulator buffers in TMEM (1 or 2)
+    int nacc;               // independent accumulators per buffer (power of 2): consecutive MMAs rotate over them
+    int raw_stages, x_stages;
+    int xkb;                // 64-K blocks per activation slot: 4, 2 or 1 (slot <= 32 KB)
+    uint32_t raw_bytes, x_kb_bytes, x_slot_bytes, x_ring_off;
     int scale_stride;       // K / block
-    int block_shift;        // log2(block / 64): K block kb uses scale column kb >> block_shift
-    int tmem_cols;
-    uint32_t x_bytes, raw_bytes;
-    uint32_t x_ring_off, raw_ring_off;   // byte offsets of the rings behind the A ring
+    int block_shift;        // log2(block / 64)
+    int vec4;               // scale / zero-point rows can be read as float4 per stage
+    int dbg;                // experiment switches (QUANTA_B200_GEMM_DBG): 1 = no MMA, 2 = no dequant math/store
 };
 
-// kAFmt: UMMA format of the dequantized A operand (0 = fp16, 1 = bf16).  fp16 A with bf16
-// activations is the mixed-format mode (selected at run time, see gemm_launch).
-template <typename ACT, int BITS, uint32_t kAFmt>
+// Contiguous range of work units of one CTA, walked tile by tile.
+struct SegWalk {
+    unsigned int u, u1, S;
+    __device__ __forceinline__ void init(const GemmParams& p, unsigned int cta) {
+        u = p.U * cta / (unsigned int)p.G; u1 = p.U * (cta + 1u) / (unsigned int)p.G; S = (unsigned int)p.S;
+    }
+    // next segment: stages [s0, s1) of `tile`; false when the range is exhausted
+    __device__ __forceinline__ bool next(int& tile, int& s0, int& s1) {
+        if (u >= u1) return false;
+        const unsigned int t = u / S;
+        const unsigned int b = u - t * S, left = u1 - u;
+        tile = (int)t; s0 = (int)b;
+        s1 = (left < S - b) ? (int)(b + left) : (int)S;
+        u += (unsigned int)(s1 - s0);
+        return true;
+    }
+};
+
+// CTA whose unit range contains unit `u`
+__device__ __forceinline__ int cta_of_unit(unsigned int u, const GemmParams& p) {
+    const unsigned int G = (unsigned int)p.G;
+    unsigned int c = (unsigned int)(((unsigned long long)u * G) / p.U);
+    while (c + 1 < G && p.U * (c + 1) / G <= u) ++c;
+    while (c > 0 && p.U * c / G > u) --c;
+    return (int)c;
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int) {
+    mbar_wait(bar, parity);          // measured: every lane polling beats one lane + reconvergence
+}
+
+template <typename ACT, int BITS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
-                  ACT* __restrict__ y, float* __restrict__ partial, const GemmParams p) {
+                  ACT* __restrict__ y, unsigned int* __restrict__ counters, float* __restrict__ partial,
+                  const __grid_constant__ GemmParams p) {
     using AT = ActTraits<ACT>;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t raw_full[kMaxRawStages], raw_empty[kMaxRawStages];
-    __shared__ uint64_t x_full[8], x_empty[8], a_full[kAStages], a_empty[kAStages], tmem_full;
+    __shared__ uint64_t raw_full[kMaxRing], raw_empty[kMaxRing], x_full[kMaxRing], x_empty[kMaxRing];
+    __shared__ uint64_t a_full[kDqGroups], a_empty[kDqGroups], d_full[2], d_empty[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int fix_flag;
+#ifdef QUANTA_GEMM_TRACE
+    __shared__ long long trace[8][48];
+    const bool tr = (p.dbg & 8) && blockIdx.x == 0;
+    int tri = 0;
+    const long long t_start = clock64();
+#define TRACE2(role, cond) do { if (tr && (cond) && tri < 48) trace[role][tri++] = clock64() - t_start; } while (0)
+#define TRACE(role) do { if (tr && tri < 48) trace[role][tri++] = clock64() - t_start; } while (0)
+#else
+#define TRACE2(role, cond) do { } while (0)
+#define TRACE(role) do { } while (0)
+#endif
 
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tile = blockIdx.x, split = blockIdx.y, m_tile = blockIdx.z;
-    const int n0 = n_tile * kTileN, m0 = m_tile * p.mb;
-    const int kb0 = split * p.kblocks_per_split;
-    const int nkb = p.kblocks_per_split;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
+    const unsigned int cta = blockIdx.x;
 
-    // shared memory: [A ring: kAStages x 16 KB][x ring: x_stages x mb*128 B][raw ring: raw_stages x 4|8 KB]
-    auto a_addr = [&](int s) { return smem + s * kATileBytes; };
-    auto x_addr = [&](int s) { return smem + p.x_ring_off + s * p.x_bytes; };
-    auto r_addr = [&](int s) { return smem + p.raw_ring_off + s * p.raw_bytes; };
+    // shared memory: [raw ring: raw_stages x 16|32 KB][x ring: x_stages x (xkb x mb x 128 B)]
+    auto r_addr = [&](int s) { return smem + (uint32_t)s * p.raw_bytes; };
+    auto x_addr = [&](int s) { return smem + p.x_ring_off + (uint32_t)s * p.x_slot_bytes; };
 
-    if (tid == 0) {
-        for (int s = 0; s < p.raw_stages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kDequantWarps); }
-        for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kDequantWarps); mbar_init(&a_empty[s], 1); }
-        mbar_init(&tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = tmem_base_slot;
+    SegWalk walk;
+    walk.init(p, cta);
+    int tile, s0, s1;
 
+    // Each producer initialises its own ring, checks in at the CTA-wide barrier without waiting
+    // (barrier.arrive) and starts streaming at once; everybody else sees all barriers after
+    // barrier.sync.  Producer loops are warp-uniform with one elected lane issuing, so the TMA
+    // operands stay in uniform registers.
     if (warp == 0) {
-        // ===== raw weight codes: deep TMA ring (bytes in flight = raw_stages x raw_bytes) =====
+        // ===== raw weight codes: deep TMA ring (bytes in flight hide the HBM latency) =====
         if (lane == 0) {
+            for (int s = 0; s < p.raw_stages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kDqGroupWarps); }
+            fence_barrier_init();
             prefetch_tensormap(&tmap_w);
-            const uint64_t pol_w = policy_evict_first();     // weights are streamed once
-            int s = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&raw_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&raw_full[s], p.raw_bytes);
-                tma_load_2d_plain(r_addr(s), &tmap_w, smem_u32(&raw_full[s]), (kb0 + i) * (kBlockK * BITS / 8), n0, pol_w);
-                if (++s == p.raw_stages) { s = 0; ph ^= 1; }
+        }
+        __syncwarp();
+        asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
+        const uint64_t pol_w = policy_evict_first();         // weights are streamed once
+        int slot = 0, issued = 0;
+        uint32_t ph = 0;
+        while (walk.next(tile, s0, s1)) {
+            const int n0 = (tile % p.n_tiles) * kTileN;
+            for (int s = s0; s < s1; ++s) {
+                if (issued >= p.raw_stages) mbar_wait(&raw_empty[slot], ph ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&raw_full[slot], p.raw_bytes);
+                    const uint32_t bar = smem_u32(&raw_full[slot]);
+                    if (BITS == 4) {
+                        tma_load_2d_plain(r_addr(slot), &tmap_w, bar, s * 128, n0, pol_w);
+                    } else {
+                        tma_load_2d_plain(r_addr(slot), &tmap_w, bar, s * 256, n0, pol_w);
+                        tma_load_2d_plain(r_addr(slot) + 16384u, &tmap_w, bar, s * 256 + 128, n0, pol_w);
+                    }
+                    TRACE(0);
+                }
+                __syncwarp();
+                ++issued;
+                if (++slot == p.raw_stages) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== activation tiles =====
+        // ===== activation tiles: xkb 64-K blocks per slot =====
         if (lane == 0) {
+            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+            fence_barrier_init();
             prefetch_tensormap(&tmap_x);
-            const uint64_t pol_x = policy_evict_last();      // activations are re-read by every CTA
-            int s = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&x_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&x_full[s], p.x_bytes);
-                tma_load_2d_plain(x_addr(s), &tmap_x, smem_u32(&x_full[s]), (kb0 + i) * kBlockK, m0, pol_x);
-                if (++s == p.x_stages) { s = 0; ph ^= 1; }
-            }
         }
-    } else if (warp == 2) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (kAFmt << 7) | (AT::kFmt << 10) |
-                                   ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
-            int sa = 0, sx = 0;
-            uint32_t pa = 0, px = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&x_full[sx], px);              // activation tile landed
-                mbar_wait(&a_full[sa], pa);              // A tile dequantized and fenced
-                tc_fence_after();
-                const uint64_t da = smem_desc_sw128(a_addr(sa));
-                const uint64_t db = smem_desc_sw128(x_addr(sx));
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);   // +32 bytes per K=16 step
-                umma_commit(&a_empty[sa]);               // both arrive when the MMAs above have read their operands
-                umma_commit(&x_empty[sx]);
-                if (++sa == kAStages) { sa = 0; pa ^= 1; }
-                if (++sx == p.x_stages) { sx = 0; px ^= 1; }
+        __syncwarp();
+        asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
+        const uint64_t pol_x = policy_evict_last();          // activations are re-read by every CTA
+        int slot = 0, issued = 0;
+        uint32_t ph = 0;
+        while (walk.next(tile, s0, s1)) {
+            const int m0 = (tile / p.n_tiles) * p.mb;
+            for (int s = s0; s < s1; ++s) {
+                for (int j = 0; j < kKbPerStage; j += p.xkb) {
+                    if (issued >= p.x_stages) mbar_wait(&x_empty[slot], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&x_full[slot], p.x_slot_bytes);
+                        // blocks past the end of K are out of bounds and arrive zero-filled
+                        for (int jj = 0; jj < p.xkb; ++jj)
+                            tma_load_2d_plain(x_addr(slot) + (uint32_t)jj * p.x_kb_bytes, &tmap_x, smem_u32(&x_full[slot]),
+                                              (s * kKbPerStage + j + jj) * kBlockK, m0, pol_x);
+                    }
+                    __syncwarp();
+                    ++issued;
+                    if (++slot == p.x_stages) { slot = 0; ph ^= 1; }
+                }
             }
-            umma_commit(&tmem_full);
         }
     } else {
-        // ===== dequantize (16 warps in 2 groups), then epilogue =====
-        // TMEM lanes are reachable per warp quarter (warp % 4); four warps share a quarter and
-        // split the batch columns in the epilogue.
-        const int quarter = warp & 3;
-        const int epart = (warp - kFirstDequantWarp) >> 2;   // epilogue: which part of the batch columns (0..3)
-        // main loop: group g handles K blocks g, g+2, ...; within the group warp dw owns weight rows
-        // [16 dw, 16 dw + 16); lane -> (row, half of the 64 K values).  Adjacent lanes read adjacent
-        // 16 bytes of raw codes and write disjoint swizzled chunks: no bank conflicts.
-        const int group = (warp - kFirstDequantWarp) / kDequantWarps;
-        const int dw = (warp - kFirstDequantWarp) % kDequantWarps;
-        const int row = 16 * dw + (lane >> 1);
-        const int half = lane & 1;
-        const int gn_d = n0 + row;
-        const float* srow = scale + (int64_t)(gn_d < p.N ? gn_d : 0) * p.scale_stride;
-        const float* zrow = zp + (int64_t)(gn_d < p.N ? gn_d : 0) * p.scale_stride;
-        // parameters of 4 consecutive scale columns at a time (one 16-byte load each)
-        const bool vec4 = (p.scale_stride & 3) == 0 && p.block_shift == 0 && (kb0 & 3) == 0 &&
-                          ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0;
-        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = s4;
-        if (vec4) {
-            s4 = __ldg(reinterpret_cast<const float4*>(srow + kb0));
-            z4 = __ldg(reinterpret_cast<const float4*>(zrow + kb0));
+        if (warp == 2) {
+            tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+        } else if (warp == 3 && lane == 0) {
+            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], kDqGroupWarps); mbar_init(&a_empty[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], kEpiWarps); }
+            fence_barrier_init();
         }
-        int s = group, r = group;                        // ring sizes are even: the group keeps its slot parity
-        uint32_t ph = 0, pr = 0;
-        for (int i = group; i < nkb; i += kDequantGroups) {
-            float sc, z;
-            if (vec4) {
-                const int e = i & 3;
-                sc = e == 0 ? s4.x : (e == 1 ? s4.y : (e == 2 ? s4.z : s4.w));
-                z = e == 0 ? z4.x : (e == 1 ? z4.y : (e == 2 ? z4.z : z4.w));
-                if (e >= 2 && i + kDequantGroups < nkb) {     // this group's next K block starts a new group of 4
-                    s4 = __ldg(reinterpret_cast<const float4*>(srow + kb0 + (i & ~3) + 4));
-                    z4 = __ldg(reinterpret_cast<const float4*>(zrow + kb0 + (i & ~3) + 4));
-                }
-            } else {
-                sc = __ldg(srow + ((kb0 + i) >> p.block_shift));
-                z = __ldg(zrow + ((kb0 + i) >> p.block_shift));
-            }
-            // raw codes -> registers, then hand the raw slot straight back to the TMA ring
-            mbar_wait(&raw_full[r], pr);
-            uint32_t w[BITS == 4 ? 4 : 8];
-            {
-                const uint32_t rrow = r_addr(r) + row * (kBlockK * BITS / 8) + (4 * BITS) * half;
-                const uint4 rv = lds128g(rrow);
-                w[0] = rv.x; w[1] = rv.y; w[2] = rv.z; w[3] = rv.w;
-                if (BITS == 8) {
-                    const uint4 rv2 = lds128g(rrow + 16);
-                    w[4] = rv2.x; w[5] = rv2.y; w[6] = rv2.z; w[7] = rv2.w;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[r]);
-            r += kDequantGroups;
-            if (r >= p.raw_stages) { r -= p.raw_stages; pr ^= 1; }
-            mbar_wait(&a_empty[s], ph ^ 1);              // the MMA that read this A slot kAStages blocks ago is done
-            const uint32_t arow = a_addr(s) + row * 128;
-            const uint32_t sw = row & 7;
-            if (BITS == 4) {
-                if (kAFmt == 0) {
-                    // fp16 A operand: packed fp16x2 math (11-bit significand keeps scale / zp accurate)
-                    const __half2 s2 = __float2half2_rn(sc), z2 = __float2half2_rn(z);
+        tc_fence_before();
+        asm volatile("barrier.sync 2, %0;" ::"n"(kGemmThreads) : "memory");
+    }
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    if (warp == 2) {
+        // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =====
+        const uint32_t idesc = (1u << 4) | (AT::kFmt << 7) | (AT::kFmt << 10) |
+                               ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+        const uint32_t kb_desc = p.x_kb_bytes >> 4;          // descriptor step between 64-K blocks of one slot
+        int sx = 0, seg = 0, sc = 0;
+        uint32_t px = 0;
+        while (walk.next(tile, s0, s1)) {
+            const int buf = p.nbuf == 2 ? (seg & 1) : 0;
+            const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);      // how often `buf` was used before
+            mbar_wait_warp(&d_empty[buf], (use & 1) ^ 1, lane);      // epilogue has drained this accumulator
+            // A dependent tcgen05.mma (same accumulator) costs ~100 cycles whatever its size, so the
+            // 16 MMAs of a stage rotate over `nacc` accumulators that the epilogue adds up.
+            const uint32_t tmem_d = tmem + kDBase + (uint32_t)(buf * p.nacc * p.mb);
+            uint32_t touched = 0;                            // accumulators already written in this segment
+            for (int s = s0; s < s1; ++s, ++sc) {
+                const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
+                const int g = sc & 1;                        // dequant group = A buffer
+                TRACE2(1, lane == 0 && sc == 0);
+                mbar_wait_warp(&a_full[g], (uint32_t)(sc >> 1) & 1u, lane);   // the stage's 4 A tiles are in TMEM
+                const uint32_t ta = tmem + (uint32_t)(g * kKbPerStage * kACols);
+                TRACE2(1, lane == 0 && sc == 0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // word = nibbles n0..n7 (8 consecutive K values); registers pair (n_i, n_{i+4})
-                        const uint32_t r0 = dq_pair<__half>(w[j] & 0x000F000Fu, s2, z2);
-                        const uint32_t r1 = dq_pair<__half>((w[j] >> 4) & 0x000F000Fu, s2, z2);
-                        const uint32_t r2 = dq_pair<__half>((w[j] >> 8) & 0x000F000Fu, s2, z2);
-                        const uint32_t r3 = dq_pair<__half>((w[j] >> 12) & 0x000F000Fu, s2, z2);
-                        const uint32_t c = 4 * half + j;                   // 16-byte chunk = 8 K values
-                        sts128(arow + ((c ^ sw) << 4), prmt_(r0, r1, 0x5410u), prmt_(r2, r3, 0x5410u),
-                               prmt_(r0, r1, 0x7632u), prmt_(r2, r3, 0x7632u));
+                for (int j = 0; j < kKbPerStage; ++j) {
+                    const int jj = j & (p.xkb - 1);
+                    if (jj == 0) mbar_wait_warp(&x_full[sx], px, lane);   // activation slot landed
+                    TRACE2(1, lane == 0 && sc == 0);
+                    tc_fence_after();
+                    TRACE2(1, lane == 0 && sc == 0);
+                    const bool live = j < nkb && !(p.dbg & 1);
+                    uint32_t acc_idx[4], acc_flag[4];        // computed by every lane: stays warp-uniform
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc_idx[k] = (uint32_t)(4 * j + k) & (uint32_t)(p.nacc - 1);
+                        acc_flag[k] = (touched >> acc_idx[k]) & 1u;
+                        if (live) touched |= 1u << acc_idx[k];
                     }
-                } else {
-                    // bf16 activations: bf16 has too few significand bits for scale / zero-point, so the
-                    // multiply-add runs in fp32.  (0x4300 | n) is the bf16 (and, shifted, the fp32) value
-                    // 128 + n; the offset is folded into the zero-point: w = (128 + n) * s + (z - 128 s).
-                    const float zf = __fmaf_rn(-128.0f, sc, z);
+                    if (elect_one()) {
+                        if (live) {
+                            const uint64_t db = smem_desc_sw128(x_addr(sx)) + (uint64_t)(jj * kb_desc);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // bytes [n0 n2 n4 n6] and [n1 n3 n5 n7]; one PRMT drops a nibble into bits 16..19 of
-                        // 0x43000000, i.e. builds the fp32 value 128 + n
-                        const uint32_t ev = w[j] & 0x0F0F0F0Fu, od = (w[j] >> 4) & 0x0F0F0F0Fu;
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            f[2 * e] = __fmaf_rn(__uint_as_float(prmt_(ev, 0x43000000u, 0x7044u | (e << 8))), sc, zf);
-                            f[2 * e + 1] = __fmaf_rn(__uint_as_float(prmt_(od, 0x43000000u, 0x7044u | (e << 8))), sc, zf);
+                            for (int k = 0; k < kBlockK / 16; ++k)        // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
+                                umma_f16_ts(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
+                                            db + 2 * k, idesc, acc_flag[k]);
                         }
-                        const uint32_t c = 4 * half + j;
-                        sts128(arow + ((c ^ sw) << 4), pack_a<kAFmt>(f[0], f[1]), pack_a<kAFmt>(f[2], f[3]),
-                               pack_a<kAFmt>(f[4], f[5]), pack_a<kAFmt>(f[6], f[7]));
+                        TRACE2(1, sc == 0);
+                        if (jj == p.xkb - 1) umma_commit(&x_empty[sx]);   // arrives when the MMAs above have read the slot
+                        if (j == kKbPerStage - 1) umma_commit(&a_empty[g]);
+                        TRACE2(1, sc == 0);
+                    }
+                    __syncwarp();
+                    if (jj == p.xkb - 1) { if (++sx == p.x_stages) { sx = 0; px ^= 1; } }
+                }
+                TRACE2(1, lane == 0 && sc == 0);
+            }
+            if (elect_one()) umma_commit(&d_full[buf]);
+            __syncwarp();
+            ++seg;
+        }
+    } else if (warp >= kFirstEpiWarp && warp < kFirstDqWarp) {
+        // ===== epilogue: TMEM lane = output feature =====
+        const int quarter = warp & 3;
+        const int row = 32 * quarter + lane;
+        const int etid = tid - 32 * kFirstEpiWarp;
+        int seg = 0;
+        while (walk.next(tile, s0, s1)) {
+            const int buf = p.nbuf == 2 ? (seg & 1) : 0;
+            const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);
+            const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+            const int gn = n_tile * kTileN + row, m0 = m_tile * p.mb;
+            const bool n_ok = gn < p.N;
+            const int m_valid = min(p.mb, p.M - m0);
+            const bool whole = (s0 == 0 && s1 == p.S);
+            const float b = (bias != nullptr && n_ok) ? AT::to_float(bias[gn]) : 0.0f;
+            // this CTA's partial slot for the tile: 0 if the tile is the first one the CTA touches, else 1
+            const unsigned int u_first = p.U * cta / (unsigned int)p.G;
+            const int which = (tile == (int)(u_first / (unsigned int)p.S)) ? 0 : 1;
+            float* mine = partial + ((size_t)cta * 2 + which) * (size_t)(kTileN * p.mb);
+
+            mbar_wait_warp(&d_full[buf], use & 1, lane);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + kDBase + (uint32_t)(buf * p.nacc * p.mb);
+            // accumulators the MMA warp wrote in this segment: 4 per 64-K block, rotating over nacc
+            const int seg_kb = min(s1 * kKbPerStage, p.total_kb) - s0 * kKbPerStage;
+            const int nv = min(p.nacc, 4 * seg_kb);
+            for (int c0 = 0; c0 < p.mb; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                for (int a = 1; a < nv; ++a) {
+                    uint32_t t[16];
+                    tmem_ld16(taddr + (uint32_t)(a * p.mb) + c0, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+                }
+                if (c0 < m_valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int m = c0 + j;
+                        if (m < m_valid) {
+                            const float v = __uint_as_float(r[j]);
+                            if (whole) { if (n_ok) y[(int64_t)(m0 + m) * p.N + gn] = AT::from_float(v + b); }
+                            else mine[m * kTileN + row] = v;
+                        }
                     }
                 }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[buf]);       // accumulator may be overwritten
+            if (!whole) {
+                // stream-K fix-up: the CTA that arrives last at the tile's counter reduces every partial
+                const unsigned int tu0 = (unsigned int)tile * (unsigned int)p.S;
+                const int c_first = cta_of_unit(tu0, p), c_last = cta_of_unit(tu0 + (unsigned int)p.S - 1u, p);
+                // release: CTA barrier, then one thread publishes with a gpu-scope fence + atomic (fences
+                // are cumulative over the barrier); acquire on the way back mirrors it
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                if (etid == 0) {
+                    __threadfence();
+                    const unsigned int old = atomicAdd(&counters[tile], 1u);
+                    __threadfence();
+                    const int last = (old == (unsigned int)(c_last - c_first)) ? 1 : 0;
+                    if (last) counters[tile] = 0u;           // leave the workspace clean for the next call
+                    fix_flag = last;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                if (fix_flag) {
+                    // thread -> 4 consecutive features, every 4th batch row; 4 rows x all contributors in flight
+                    const int f4 = 4 * (etid & 31), mq = etid >> 5;
+                    const int gn4 = n_tile * kTileN + f4;
+                    float b4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? AT::to_float(bias[gn4 + e]) : 0.0f;
+                    const size_t slot_elems = (size_t)(kTileN * p.mb);
+                    const bool vec_ok = (p.N & 3) == 0 && gn4 + 3 < p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+                    for (int mb0 = mq; mb0 < m_valid; mb0 += 16) {
+                        float4 acc[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int c = c_first; c <= c_last; ++c) {
+                            const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / (unsigned int)p.S)) ? 0 : 1;
+                            const float* src = partial + ((size_t)c * 2 + wc) * slot_elems + f4;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int m = mb0 + 4 * i;
+                                if (m < m_valid) {
+                                    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + m * kTileN));
+                                    acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int m = mb0 + 4 * i;
+                            if (m < m_valid) {
+                                ACT* dst = y + (int64_t)(m0 + m) * p.N + gn4;
+                                const float o[4] = {acc[i].x + b4[0], acc[i].y + b4[1], acc[i].z + b4[2], acc[i].w + b4[3]};
+                                if (vec_ok) {
+                                    uint2 pk;
+                                    pk.x = AT::pack(o[0], o[1]);
+                                    pk.y = AT::pack(o[2], o[3]);
+                                    *reinterpret_cast<uint2*>(dst) = pk;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                                }
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // fix_flag is reused
+            }
+            ++seg;
+        }
+    } else if (warp >= kFirstDqWarp) {
+        // ===== dequantize: thread = (weight row = TMEM lane, half of each 64-K block) =====
+        using V2 = typename AT::V2;
+        const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = ((warp - kFirstDqWarp) >> 2) & 1;            // which 32 of the 64 K values
+        const int group = (warp - kFirstDqWarp) / kDqGroupWarps;      // stages group, group + 2, ...
+        const int row = 32 * quarter + lane;
+        // this group's A buffer: 4 tiles of 32 columns; this thread's half tile starts 16 columns in
+        const uint32_t a_addr = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(group * kKbPerStage * kACols + 16 * half);
+        const V2 c2 = AT::dup(AT::kCentre);
+        // scale / zero-point of the group's next stage, loaded one stage of work ahead
+        SegWalk ahead = walk;
+        int a_tile = 0, a_s = 0, a_s1 = 0;
+        bool a_ok = ahead.next(a_tile, a_s, a_s1);
+        float sv[4], zv[4];
+        auto fetch_params = [&](int t, int s) {
+            const int gn = (t % p.n_tiles) * kTileN + row;
+            const int64_t rbase = (int64_t)(gn < p.N ? gn : p.N - 1) * p.scale_stride;
+            const int kb = s * kKbPerStage;
+            if (p.vec4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(scale + rbase + kb));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(zp + rbase + kb));
+                sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
+                zv[0] = c.x; zv[1] = c.y; zv[2] = c.z; zv[3] = c.w;
             } else {
-                // this thread's 32 K values = 32 code bytes (w[0..7])
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        // q exact via the 2^23 magic; q*scale + zp with one fp32 rounding (the reference rounds
-                        // twice: <= 1 fp32 ulp apart, far inside the 16-bit rounding that follows)
-                        const uint32_t word = w[2 * j + (e >> 2)];
-                        const float q = __fsub_rn(__uint_as_float(prmt_(word, 0x4B000000u, 0x7540u + (e & 3))), 8388608.0f);
-                        f[e] = __fmaf_rn(q, sc, z);
-                    }
-                    const uint32_t c = 4 * half + j;
-                    sts128(arow + ((c ^ sw) << 4), pack_a<kAFmt>(f[0], f[1]), pack_a<kAFmt>(f[2], f[3]),
-                           pack_a<kAFmt>(f[4], f[5]), pack_a<kAFmt>(f[6], f[7]));
+                    const int col = min(kb + j, p.total_kb - 1) >> p.block_shift;
+                    sv[j] = __ldg(scale + rbase + col);
+                    zv[j] = __ldg(zp + rbase + col);
                 }
             }
-            fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[s]);
-            s += kDequantGroups;
-            if (s >= kAStages) { s -= kAStages; ph ^= 1; }
-        }
+        };
+        // advance `ahead` by n stages (across segments)
+        auto skip = [&](int n) {
+            while (a_ok && n > 0) {
+                const int room = a_s1 - a_s;
+                if (n < room) { a_s += n; n = 0; }
+                else { n -= room; a_ok = ahead.next(a_tile, a_s, a_s1); }
+            }
+        };
+        skip(group);
+        if (a_ok) fetch_params(a_tile, a_s);
 
-        // ---- epilogue: TMEM lane = output feature; the quarter's two warps split the batch columns ----
-        mbar_wait(&tmem_full, 0);
-        tc_fence_after();
-        const int gn = n0 + 32 * quarter + lane;
-        const bool n_ok = gn < p.N;
-        const uint32_t taddr = tmem_d + ((uint32_t)(32 * quarter) << 16);
-        const float b = (bias != nullptr && n_ok && p.split_k == 1) ? AT::to_float(bias[gn]) : 0.0f;
-        // mb is a multiple of 16: 4 column parts when mb % 32 == 0, else 2 parts (8-column TMEM loads)
-        const int nparts = (p.mb & 31) == 0 ? 4 : 2;
-        const int cpp = p.mb / nparts;
-        const int c_begin = epart < nparts ? epart * cpp : 0, c_end = epart < nparts ? c_begin + cpp : 0;
-        for (int c0 = c_begin; c0 < c_end; c0 += 8) {
-            uint32_t r[8];
-            tmem_ld8(taddr + c0, r);
-            tmem_ld_wait();
-            if (n_ok) {
+        int sc = 0;                 // global stage counter of this CTA
+        int rslot = 0;
+        uint32_t rph = 0;
+        while (walk.next(tile, s0, s1)) {
+            for (int s = s0; s < s1; ++s, ++sc) {
+                if ((sc & (kDqGroups - 1)) == group) {
+                    const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
+                    float cs[4], cz[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int m = m0 + c0 + j;
-                    if (m < p.M) {
-                        const float v = __uint_as_float(r[j]);
-                        if (p.split_k == 1) y[(int64_t)m * p.N + gn] = AT::from_float(v + b);
-                        else partial[((int64_t)split * p.M + m) * p.N + gn] = v;
+                    for (int j = 0; j < 4; ++j) { cs[j] = sv[j]; cz[j] = zv[j]; }
+                    if (cs[0] == 12345.0f) TRACE(2 + 3 * group);   // forces the parameter loads to complete here
+                    if (lane == 0 && quarter == 0 && half == 0) TRACE(2 + 3 * group);
+                    skip(kDqGroups);
+                    if (a_ok) fetch_params(a_tile, a_s);     // lands while this stage is processed
+                    mbar_wait_warp(&raw_full[rslot], rph, lane);
+                    if (lane == 0 && quarter == 0 && half == 0) TRACE(2 + 3 * group);
+                    const uint32_t rrow = r_addr(rslot) + (uint32_t)row * 128u;
+                    const uint32_t sw = (uint32_t)(row & 7);
+                    // the MMAs that read this group's A buffer two stages ago are done
+                    mbar_wait_warp(&a_empty[group], ((uint32_t)(sc >> 1) & 1u) ^ 1u, lane);
+                    tc_fence_after();
+                    if (lane == 0 && quarter == 0 && half == 0) TRACE(3 + 3 * group);
+#pragma unroll
+                    for (int j = 0; j < kKbPerStage; ++j) {
+                        if (j < nkb && !(p.dbg & 2)) {
+                            uint32_t out[16];
+                            if (BITS == 4) {
+                                const V2 s2 = AT::dup(cs[j]);
+                                const V2 z2 = AT::dup(__fmaf_rn(8.0f, cs[j], cz[j]));
+                                const uint4 rv = lds128g(rrow + (((uint32_t)(2 * j + half) ^ sw) << 4));
+                                dequant_word4<ACT>(rv.x, s2, z2, c2, out);
+                                dequant_word4<ACT>(rv.y, s2, z2, c2, out + 4);
+                                dequant_word4<ACT>(rv.z, s2, z2, c2, out + 8);
+                                dequant_word4<ACT>(rv.w, s2, z2, c2, out + 12);
+                            } else {
+                                const float zc = __fmaf_rn(-32768.0f, cs[j], cz[j]);
+                                const uint32_t box = rrow + (uint32_t)(j >> 1) * 16384u;
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint4 rv = lds128g(box + (((uint32_t)(4 * (j & 1) + 2 * half + h) ^ sw) << 4));
+                                    dequant_word8<ACT>(rv.x, cs[j], zc, out + 8 * h);
+                                    dequant_word8<ACT>(rv.y, cs[j], zc, out + 8 * h + 2);
+                                    dequant_word8<ACT>(rv.z, cs[j], zc, out + 8 * h + 4);
+                                    dequant_word8<ACT>(rv.w, cs[j], zc, out + 8 * h + 6);
+                                }
+                            }
+                            tmem_st16(a_addr + (uint32_t)(j * kACols), out);
+                        }
                     }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&a_full[group]);
+                        mbar_arrive(&raw_empty[rslot]);
+                    }
+                    if (lane == 0 && quarter == 0 && half == 0) TRACE(4 + 3 * group);
                 }
+                if (++rslot == p.raw_stages) { rslot = 0; rph ^= 1; }
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_d, p.tmem_cols); }
-}
-
-// y[m,n] = sum_s partial[s][m][n] + bias[n]
-template <typename ACT>
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, const ACT* __restrict__ bias,
-                                                            ACT* __restrict__ y, int64_t MN, int N, int split_k) {
-    using AT = ActTraits<ACT>;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= MN) return;
-    float acc = 0.0f;
-    for (int s = 0; s < split_k; ++s) acc += partial[(int64_t)s * MN + i];
-    if (bias) acc += AT::to_float(bias[i % N]);
-    y[i] = AT::from_float(acc);
-}
-
-constexpr int kMaxSplitK = 8;
-
-// Pick the K split that minimises (waves over the 148 SMs) x (K blocks per CTA + fixed
-// prologue/epilogue cost, ~6 K-block equivalents); ties go to the smaller split.
-static int choose_split_k(int n_tiles, int m_tiles, int total_kblocks) {
-    int best = 1;
-    int64_t best_cost = -1;
-    for (int s = 1; s <= kMaxSplitK; ++s) {
-        if (total_kblocks % s) continue;
-        if (s > 1 && total_kblocks / s < 4) break;
-        const int64_t ctas = (int64_t)n_tiles * m_tiles * s;
-        const int64_t waves = (ctas + kNumSMs - 1) / kNumSMs;
-        const int64_t cost = waves * (total_kblocks / s + 6);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
+#ifdef QUANTA_GEMM_TRACE
+    if (tr && tid == 0) {
+        printf("end %lld\n", clock64() - t_start);
+        for (int r = 0; r < 8; ++r) { printf("role %d:", r); for (int i = 0; i < 48; ++i) printf(" %lld", trace[r][i]); printf("\n"); }
     }
-    return best;
+#endif
 }
+
+// ---- host side --------------------------------------------------------------
 
 size_t gemm_workspace_bytes(int64_t M, int64_t N);
-size_t gemm_workspace_bytes(int64_t M, int64_t N) {
-    return (size_t)kMaxSplitK * (size_t)M * (size_t)N * sizeof(float) + 512;     // fp32 split-K partials
+size_t gemm_workspace_bytes(int64_t M, int64_t) {
+    int64_t mb = (M + 15) / 16 * 16;
+    if (mb > 256) mb = 256;
+    return (size_t)kCounterBytes + (size_t)kNumSMs * 2 * kTileN * (size_t)mb * sizeof(float) + 512;
 }
 size_t int8_outlier_workspace_bytes(int64_t, int64_t) { return 256; }
 
-template <typename ACT, int BITS, uint32_t kAFmt>
-static cudaError_t launch_gemm_kernel(dim3 grid, int smem, cudaStream_t st, const CUtensorMap& tw, const CUtensorMap& tx,
-                                      const float* scale, const float* zp, const ACT* bias, ACT* y, float* partial,
-                                      const GemmParams& p) {
-    auto kern = gemm_wna16_kernel<ACT, BITS, kAFmt>;
-    static int smem_set = 0;
-    if (smem > smem_set) {           // static __shared__ (barriers) also counts against the 227 KB opt-in limit
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        smem_set = smem;
-    }
-    kern<<<grid, kGemmThreads, smem, st>>>(tw, tx, scale, zp, bias, y, partial, p);
-    return cudaGetLastError();
+// Number of CTAs: every SM with equal contiguous unit ranges (stream-K), or tiles x s CTAs whose
+// ranges coincide with tile boundaries (s = 1: no partials at all).  Costs in SM cycles, from
+// the measurements in DESIGN.md: a stage (256 K) costs the MMA warp ~600 cycles of barrier
+// traffic plus 16 MMAs of max(70, mb/2) cycles each, the dequant groups ~650 cycles, and one SM
+// pulls its raw codes and activation tiles (re-read by every tile) out of L2 at ~29 B/cycle;
+// a partial costs its fp32 store, ~4000 cycles of release/acquire latency and the last
+// arriver's reads of every contributor's tile at ~32 B/cycle.
+static int choose_ctas(int tiles, int S, int mb, int raw_bytes) {
+    const long long U = (long long)tiles * S;
+    const double mma = 600.0 + 16.0 * (mb / 2.0 > 70.0 ? mb / 2.0 : 70.0);
+    const double pull = (512.0 * mb + raw_bytes) / 29.0;
+    const double stage = fmax(fmax(mma, 650.0), pull);
+    const double tile_io = (double)kTileN * mb * 4.0 / 32.0;
+    int best = 1;
+    double best_cost = -1.0;
+    auto consider = [&](int G) {
+        if (G < 1 || G > kNumSMs || (long long)G > U) return;
+        double cost = (double)((U + G - 1) / G) * stage;
+        if (G != tiles) {
+            const double contributors = (double)G / tiles < 2.0 ? 2.0 : (double)G / tiles + 1.0;
+            cost += 4000.0 + tile_io * (1.0 + contributors);
+        }
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
+    };
+    consider(tiles <= kNumSMs ? tiles : 0);
+    for (int s = 2; tiles * s <= kNumSMs && s <= S; ++s) consider(tiles * s);
+    consider((int)(U < kNumSMs ? U : kNumSMs));
+    return best;
 }
 
 template <typename ACT, int BITS>
@@ -451,66 +700,67 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     int mb = (int)((M + 15) / 16 * 16);
     if (mb > 256) mb = 256;
     p.mb = mb;
-    const int m_tiles = (int)((M + mb - 1) / mb);
-    const int n_tiles = (int)((N + kTileN - 1) / kTileN);
-    const int total_kb = (int)(K / kBlockK);
-    int split = choose_split_k(n_tiles, m_tiles, total_kb);
-    if (const char* e = getenv("QUANTA_B200_SPLIT_K")) { int v = atoi(e); if (v >= 1 && total_kb % v == 0) split = v; }
-    p.split_k = split;
-    p.kblocks_per_split = total_kb / split;
+    p.m_tiles = (int)((M + mb - 1) / mb);
+    p.n_tiles = (int)((N + kTileN - 1) / kTileN);
+    p.total_kb = (int)(K / kBlockK);
+    p.S = (p.total_kb + kKbPerStage - 1) / kKbPerStage;
+    const int tiles = p.n_tiles * p.m_tiles;
+    if (tiles > kMaxTiles) return QUANTA_EUNSUPPORTED;
+    if ((unsigned long long)tiles * (unsigned long long)p.S * (unsigned long long)(kNumSMs + 1) >= (1ull << 32)) return QUANTA_EUNSUPPORTED;
+    p.U = (unsigned int)tiles * (unsigned int)p.S;
+    p.G = choose_ctas(tiles, p.S, mb, BITS == 4 ? 16384 : 32768);
+    if (const char* e = getenv("QUANTA_B200_GEMM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= kNumSMs && (unsigned int)v <= p.U) p.G = v; }
+    // accumulators: nbuf x nacc x mb <= 256 TMEM columns
+    p.nacc = mb <= 16 ? 8 : (mb <= 64 ? 4 : (mb <= 128 ? 2 : 1));
+    p.nbuf = (2 * p.nacc * mb <= kTmemCols - kDBase) ? 2 : 1;
+    p.dbg = 0;
+    if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
     p.scale_stride = (int)(K / block);
     int bs = 0; while ((int64_t)(kBlockK << bs) < block) ++bs;
     p.block_shift = bs;
-    p.x_bytes = (uint32_t)mb * 128u;
-    p.raw_bytes = (uint32_t)(kTileN * kBlockK * BITS / 8);
-    // Shared-memory budget: a shallow A ring (dequant -> MMA latency only), an activation ring, and
-    // everything else for the raw-code ring: raw bytes in flight are what hides the HBM latency.
-    const uint32_t budget = 218u * 1024u;
-    const uint32_t a_ring = (uint32_t)kAStages * kATileBytes;
-    int x_stages = mb <= 64 ? 8 : (mb <= 128 ? 4 : 3);
-    int raw_stages = (int)((budget - a_ring - x_stages * p.x_bytes) / p.raw_bytes);
-    if (raw_stages > kMaxRawStages) raw_stages = kMaxRawStages;
-    raw_stages &= ~1;                                    // the two dequant groups alternate slots
+    p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
+              ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
+    p.x_kb_bytes = (uint32_t)mb * 128u;
+    p.xkb = mb <= 64 ? 4 : (mb <= 128 ? 2 : 1);              // activation slots of at most 32 KB
+    p.x_slot_bytes = p.x_kb_bytes * (uint32_t)p.xkb;
+    p.raw_bytes = BITS == 4 ? 16384u : 32768u;
+    // Shared-memory budget: an activation ring sized for the MMA, everything else for the raw-code
+    // ring — raw bytes in flight are what hides the HBM latency.
+    const uint32_t budget = 214u * 1024u;
+    int x_stages = mb <= 16 ? 6 : (mb <= 32 ? 4 : (mb <= 64 ? 3 : 4));      // 48 / 64 / 96 / 128 KB
+    int raw_stages = (int)((budget - (uint32_t)x_stages * p.x_slot_bytes) / p.raw_bytes);
+    if (raw_stages > kMaxRing) raw_stages = kMaxRing;
+    raw_stages &= ~1;                  // even: a raw slot is always consumed by the same dequant group
     if (raw_stages < 2) return QUANTA_EUNSUPPORTED;
     p.raw_stages = raw_stages;
     p.x_stages = x_stages;
-    p.x_ring_off = a_ring;
-    p.raw_ring_off = a_ring + (uint32_t)x_stages * p.x_bytes;
-    int cols = 32; while (cols < mb) cols <<= 1;
-    p.tmem_cols = cols;
-    float* partial = nullptr;
-    if (split > 1) {
-        const size_t need = (size_t)split * M * N * sizeof(float);
-        if (!workspace || ws_bytes < need + 256) return QUANTA_EWORKSPACE;
-        partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-    }
+    p.x_ring_off = (uint32_t)raw_stages * p.raw_bytes;
+
+    const size_t need = (size_t)kCounterBytes + (size_t)p.G * 2 * kTileN * (size_t)mb * sizeof(float) + 256;
+    if (!workspace || ws_bytes < need) return QUANTA_EWORKSPACE;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    float* partial = reinterpret_cast<float*>(ws + kCounterBytes);
 
     CUtensorMap tmap_w, tmap_x;
     const uint64_t wrow_bytes = (uint64_t)K * BITS / 8;
     int rc = make_tensor_map_2d(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wq, wrow_bytes, (uint64_t)N, wrow_bytes,
-                                (uint32_t)(kBlockK * BITS / 8), kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
+                                128, kTileN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_tensor_map_2d(&tmap_x, ActTraits<ACT>::kTma, 2, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK,
                             (uint32_t)mb, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
-    // A-operand format = activation format.  (A mixed fp16-A x bf16-B MMA was tried so that bf16
-    // activations could use the cheaper packed-fp16 dequant math: tcgen05.mma kind::f16 raises an
-    // illegal-instruction fault on sm_100a when the A and B formats differ.)
-    const int smem = (int)(p.raw_ring_off + (uint32_t)p.raw_stages * p.raw_bytes + 1024);
-    dim3 grid(n_tiles, split, m_tiles);
-    cudaError_t e;
-    if (ActTraits<ACT>::kFmt == 0)
-        e = launch_gemm_kernel<ACT, BITS, 0>(grid, smem, st, tmap_w, tmap_x, scale, zp, bias, y, partial, p);
-    else
-        e = launch_gemm_kernel<ACT, BITS, 1>(grid, smem, st, tmap_w, tmap_x, scale, zp, bias, y, partial, p);
-    if (e != cudaSuccess) return (int)e;
-    if (split > 1) {
-        const int64_t MN = M * N;
-        splitk_reduce_kernel<ACT><<<(unsigned)((MN + 255) / 256), 256, 0, st>>>(partial, bias, y, MN, (int)N, split);
-        e = cudaGetLastError();
+    auto kern = gemm_wna16_kernel<ACT, BITS>;
+    const int smem = (int)(p.x_ring_off + (uint32_t)p.x_stages * p.x_slot_bytes + 1024);
+    static int smem_set = 0;           // per instantiation
+    if (smem > smem_set) {             // static __shared__ (barriers) also counts against the 227 KB opt-in limit
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_set = smem;
     }
-    return cuda_status(e);
+    kern<<<p.G, kGemmThreads, smem, st>>>(tmap_w, tmap_x, scale, zp, bias, y, counters, partial, p);
+    return cuda_status(cudaGetLastError());
 }
 
 }  // namespace quanta

@@ -35,7 +35,7 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
     if bias is not None:
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     with torch.cuda.device(dev):
-        ws = _host.workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+        ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
         st = _lib.lib().quanta_gemm_wna16(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits, scale.data_ptr(),
                                           zp.data_ptr(), blocksize, bias.data_ptr() if bias is not None else None,
                                           y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
