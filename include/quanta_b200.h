@@ -61,7 +61,10 @@ QUANTA_API int         quanta_abi_version(void);
 QUANTA_API const char* quanta_error_string(int code);
 
 /* Bytes of device workspace needed by `op` on a [rows, cols] problem
- * (for QUANTA_OP_GEMM / INT8_OUTLIER: rows = M, cols = N).  Always >= 256. */
+ * (QUANTA_OP_GEMM: rows = M, cols = N;  QUANTA_OP_INT8_OUTLIER: rows = M,
+ * cols = K).  Always >= 256.  The first 64 KB of the QUANTA_OP_GEMM workspace
+ * hold arrival counters: they must be zero before the first call and every
+ * call leaves them zero (allocate the buffer zero-filled, once).          */
 QUANTA_API size_t quanta_workspace_bytes(int op, int64_t rows, int64_t cols);
 
 /* ---- convention A: Quanta/functional/quantization.py "linear" -------------

@@ -316,8 +316,10 @@ def int8_outlier_matmul(x, qw, cw, threshold=6.0, bias=None, act_dtype="bf16"):
         am = np.max(np.abs(xr), axis=1, keepdims=True).astype(np.float32)
         cx = ((F32(1) / am).astype(np.float32) * F32(127)).astype(np.float32)
         cx = np.where(am == 0, F32(1), cx).astype(np.float32)
-        qx = np.clip(np.rint((xr * cx).astype(np.float32)), -127, 127).astype(np.int64)
-        acc = qx @ qw.astype(np.int64).T                                       # fits int32
+        qx = np.clip(np.rint((xr * cx).astype(np.float32)), -127, 127).astype(np.float64)
+        # integer products summed in float64: every partial sum is an integer < 2^53, hence exact
+        # (|acc| <= 127 * 127 * K fits int32), and BLAS makes it fast
+        acc = qx @ qw.astype(np.float64).T
         denom = (cx * cw.reshape(1, -1)).astype(np.float32)
         y = (acc.astype(np.float32) / denom).astype(np.float32).astype(np.float64)
         if J.size:

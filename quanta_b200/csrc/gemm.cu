@@ -659,7 +659,6 @@ size_t gemm_workspace_bytes(int64_t M, int64_t) {
     if (mb > 256) mb = 256;
     return (size_t)kCounterBytes + (size_t)kNumSMs * 2 * kTileN * (size_t)mb * sizeof(float) + 512;
 }
-size_t int8_outlier_workspace_bytes(int64_t, int64_t) { return 256; }
 
 // Number of CTAs: every SM with equal contiguous unit ranges (stream-K), or tiles x s CTAs whose
 // ranges coincide with tile boundaries (s = 1: no partials at all).  Costs in SM cycles, from
@@ -787,9 +786,4 @@ extern "C" int quanta_gemm_wna16(const void* x, int act_dtype, const uint8_t* wq
                          : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, (T*)y, M, N, K, workspace, workspace_bytes, st);
     }
     return QUANTA_EINVAL;
-}
-
-extern "C" int quanta_int8_outlier_matmul(const void*, int, const int8_t*, const float*, float, const void*, void*,
-                                          int64_t, int64_t, int64_t, void*, size_t, void*) {
-    return QUANTA_EUNSUPPORTED;
 }

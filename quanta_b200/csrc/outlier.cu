@@ -1,0 +1,336 @@
+// LLM.int8()-style outlier-split matmul (row G3 of SURVEY §8) behind
+// Linear8bitLt.threshold (Quanta/nn/linear.py:20,25 — stored, never used by the
+// reference; semantics defined by oracle/oracle_np.py:int8_outlier_matmul).
+//
+//   J  = { j : max_i |x[i,j]| > threshold }                       outlier feature columns
+//   cx[i] = rcp(absmax_i over non-outlier columns) * 127           (B1-symmetric arithmetic)
+//   qx[i,k] = clamp(rint(x[i,k] * cx[i]), -127, 127), 0 for k in J
+//   y[i,n] = float(sum_k qx[i,k] qw[n,k]) / (cx[i] * cw[n])        int8 x int8 -> int32 on the tensor cores
+//          + sum_{j in J} x[i,j] * round_act(qw[n,j] / cw[n])      16-bit part, fp32 accumulate
+//          + bias[n]
+//
+// Launches on the caller's stream:
+//   1. outlier_colmax_kernel + outlier_columns_kernel   column abs-max of x, flags, ordered list J
+//   2. outlier_rowquant_kernel  per-row abs-max over non-outlier columns, cx, int8 codes qx
+//   3. int8_gemm_kernel         tcgen05.mma.kind::i8 (A = qw, B = qx, both TMA-fed, SWIZZLE_128B),
+//                               int32 accumulators in TMEM; the epilogue rescales, adds the
+//                               outlier columns on the CUDA cores and stores y
+#include "common.cuh"
+
+namespace quanta {
+
+constexpr int kOTileN = 128;      // output features per CTA (UMMA M)
+constexpr int kOBlockK = 128;     // int8 K values per stage: one 128-byte swizzle atom
+constexpr int kOThreads = 32 * 6; // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+constexpr int kOMaxStages = 8;
+
+template <typename T> __device__ __forceinline__ float ld_act(const T* p);
+template <> __device__ __forceinline__ float ld_act<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ float round_act(float v);
+template <> __device__ __forceinline__ float round_act<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float round_act<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+template <typename T> __device__ __forceinline__ T to_act(float v);
+template <> __device__ __forceinline__ __half to_act<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_act<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 1. outlier columns ------------------------------------------------------
+// 1a. column abs-max: thread = column (coalesced across the CTA), blockIdx.y = chunk of 64 rows;
+//     non-negative floats order like their bit patterns, so the chunks merge with atomicMax.
+template <typename ACT>
+__global__ void __launch_bounds__(256) outlier_colmax_kernel(const ACT* __restrict__ x, int M, int K,
+                                                             unsigned int* __restrict__ colmax) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= K) return;
+    const int r0 = blockIdx.y * 64, r1 = min(M, r0 + 64);
+    float mx = 0.0f;
+    for (int i = r0; i < r1; ++i) mx = fmaxf(mx, fabsf(ld_act(x + (int64_t)i * K + c)));
+    atomicMax(colmax + c, __float_as_uint(mx));
+}
+
+// 1b. flags and the ordered list J: one CTA, block-wide exclusive scan per 1024 columns.
+__global__ void __launch_bounds__(1024) outlier_columns_kernel(const unsigned int* __restrict__ colmax, int K, float threshold,
+                                                               uint8_t* __restrict__ flag, int* __restrict__ jlist,
+                                                               int* __restrict__ jcount) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < K; c0 += 1024) {
+        const int c = c0 + threadIdx.x;
+        int f = 0;
+        if (c < K) {
+            f = __uint_as_float(colmax[c]) > threshold ? 1 : 0;
+            flag[c] = (uint8_t)f;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, f);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int in_warp = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) warp_sums[w] = __popc(ballot);
+        __syncthreads();
+        int before = 0;
+        for (int k = 0; k < w; ++k) before += warp_sums[k];
+        const int b = base;
+        if (f) jlist[b + before + in_warp] = c;
+        __syncthreads();
+        if (threadIdx.x == 1023) base = b + before + __popc(ballot);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *jcount = base;
+}
+
+// ---- 2. per-row int8 codes of the non-outlier part ----------------------------
+template <typename ACT>
+__global__ void __launch_bounds__(256) outlier_rowquant_kernel(const ACT* __restrict__ x, int K,
+                                                               const uint8_t* __restrict__ flag,
+                                                               float* __restrict__ cx, int8_t* __restrict__ qx) {
+    const int i = blockIdx.x;
+    const ACT* xr = x + (int64_t)i * K;
+    float am = 0.0f;
+    for (int k = threadIdx.x; k < K; k += 256) if (!flag[k]) am = fmaxf(am, fabsf(ld_act(xr + k)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = am;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) am = fmaxf(am, red[w]);
+    // backends/cpu/quantization.py:44-47: scale = 127 / absmax == reciprocal(absmax) * 127
+    const float c = am == 0.0f ? 1.0f : __fmul_rn(__frcp_rn(am), 127.0f);
+    if (threadIdx.x == 0) cx[i] = c;
+    int8_t* qr = qx + (int64_t)i * K;
+    for (int k = threadIdx.x; k < K; k += 256) {
+        float v = flag[k] ? 0.0f : __fmul_rn(ld_act(xr + k), c);
+        v = fminf(fmaxf(rintf(v), -127.0f), 127.0f);
+        qr[k] = (int8_t)(int)v;
+    }
+}
+
+// ---- 3. int8 x int8 -> int32 GEMM + epilogue ------------------------------------
+__device__ __forceinline__ void tma_load_2d_o(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ bool elect_one_o() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+struct OutlierParams {
+    int M, N, K;
+    int mb;           // UMMA N: batch rows per CTA (multiple of 16, <= 256)
+    int stages;
+    int tmem_cols;
+    uint32_t a_bytes, b_bytes;
+};
+
+template <typename ACT>
+__global__ void __launch_bounds__(kOThreads, 1)
+int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                 const ACT* __restrict__ x, const int8_t* __restrict__ qw, const float* __restrict__ cw,
+                 const float* __restrict__ cx, const int* __restrict__ jlist, const int* __restrict__ jcount,
+                 const ACT* __restrict__ bias, ACT* __restrict__ y, const __grid_constant__ OutlierParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full[kOMaxStages], empty[kOMaxStages], d_full;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n0 = blockIdx.x * kOTileN, m0 = blockIdx.y * p.mb;
+    const int nk = (p.K + kOBlockK - 1) / kOBlockK;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&d_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: weight codes [128 x 128 B] and activation codes [mb x 128 B] per stage =====
+        if (lane == 0) { prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_x); }
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < nk; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one_o()) {
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                const uint32_t dst = smem + (uint32_t)s * stage_bytes;
+                tma_load_2d_o(dst, &tmap_w, smem_u32(&full[s]), kb * kOBlockK, n0);
+                tma_load_2d_o(dst + p.a_bytes, &tmap_x, smem_u32(&full[s]), kb * kOBlockK, m0);
+            }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: 4 x (K = 32) tcgen05.mma.kind::i8 per stage =====
+        // instruction descriptor: D = S32, A = B = signed int8, K-major, N = mb, M = 128
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)(kOTileN >> 4) << 24);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < nk; ++kb) {
+            mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one_o()) {
+                const uint64_t da = desc_sw128(smem + (uint32_t)s * stage_bytes);
+                const uint64_t db = desc_sw128(smem + (uint32_t)s * stage_bytes + p.a_bytes);
+#pragma unroll
+                for (int k = 0; k < kOBlockK / 32; ++k) {
+                    const uint32_t acc = (kb != 0 || k != 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+                        "}\n" ::"r"(tmem), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(acc) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+                if (kb == nk - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&d_full)) : "memory");
+            }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else {
+        // ===== epilogue: TMEM lane = output feature =====
+        const int quarter = warp & 3;
+        const int gn = n0 + 32 * quarter + lane;
+        const bool n_ok = gn < p.N;
+        const float cwn = n_ok ? cw[gn] : 1.0f;
+        const float b = (bias != nullptr && n_ok) ? ld_act(bias + gn) : 0.0f;
+        const int nj = *jcount;
+        const int8_t* qrow = qw + (int64_t)(n_ok ? gn : 0) * p.K;
+        mbar_wait(&d_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16);
+        const int m_valid = min(p.mb, p.M - m0);
+        for (int c0 = 0; c0 < p.mb; c0 += 16) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr + c0) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 >= m_valid) continue;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int m = m0 + c0 + j;
+                const float cxm = (c0 + j < m_valid) ? cx[m] : 1.0f;
+                // float(acc) / (cx * cw): true divide by the rounded product (oracle arithmetic)
+                v[j] = __fdiv_rn((float)(int)r[j], __fmul_rn(cxm, cwn));
+            }
+            // outlier columns: x[m, j] * round_act(qw[n, j] / cw[n]), fp32 accumulate
+            for (int t = 0; t < nj; ++t) {
+                const int jc = jlist[t];
+                const float wo = round_act<ACT>(__fdiv_rn((float)qrow[jc], cwn));
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < m_valid) v[j] = __fmaf_rn(ld_act(x + (int64_t)(m0 + c0 + j) * p.K + jc), wo, v[j]);
+            }
+            if (n_ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < m_valid) y[(int64_t)(m0 + c0 + j) * p.N + gn] = to_act<ACT>(v[j] + b);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// workspace: [flags K][colmax K uints][jcount + jlist (K+1 ints)][cx M floats][qx M*K bytes]
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+size_t int8_outlier_workspace_bytes(int64_t M, int64_t K) {
+    return align256((size_t)K) + align256((size_t)K * 4) + align256((size_t)(K + 1) * 4) + align256((size_t)M * 4) + align256((size_t)M * (size_t)K) + 512;
+}
+
+template <typename ACT>
+static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float threshold, const ACT* bias, ACT* y,
+                          int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < int8_outlier_workspace_bytes(M, K)) return QUANTA_EWORKSPACE;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    uint8_t* flag = ws;
+    unsigned int* colmax = reinterpret_cast<unsigned int*>(ws + align256((size_t)K));
+    int* jcount = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(colmax) + align256((size_t)K * 4));
+    int* jlist = jcount + 1;
+    float* cx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(jcount) + align256((size_t)(K + 1) * 4));
+    int8_t* qx = reinterpret_cast<int8_t*>(reinterpret_cast<uint8_t*>(cx) + align256((size_t)M * 4));
+
+    cudaError_t me = cudaMemsetAsync(colmax, 0, (size_t)K * 4, st);
+    if (me != cudaSuccess) return (int)me;
+    outlier_colmax_kernel<ACT><<<dim3((unsigned)((K + 255) / 256), (unsigned)((M + 63) / 64)), 256, 0, st>>>(x, (int)M, (int)K, colmax);
+    outlier_columns_kernel<<<1, 1024, 0, st>>>(colmax, (int)K, threshold, flag, jlist, jcount);
+    outlier_rowquant_kernel<ACT><<<(unsigned)M, 256, 0, st>>>(x, (int)K, flag, cx, qx);
+
+    OutlierParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    int mb = (int)((M + 15) / 16 * 16);
+    if (mb > 256) mb = 256;
+    p.mb = mb;
+    p.a_bytes = kOTileN * kOBlockK;
+    p.b_bytes = (uint32_t)mb * kOBlockK;
+    int stages = (int)((200u * 1024u) / (p.a_bytes + p.b_bytes));
+    if (stages > kOMaxStages) stages = kOMaxStages;
+    p.stages = stages;
+    int cols = 32; while (cols < mb) cols <<= 1;
+    p.tmem_cols = cols;
+
+    CUtensorMap tmap_w, tmap_x;
+    int rc = make_tensor_map_2d(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, qw, (uint64_t)K, (uint64_t)N, (uint64_t)K, kOBlockK,
+                                kOTileN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, qx, (uint64_t)K, (uint64_t)M, (uint64_t)K, kOBlockK,
+                            (uint32_t)mb, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    auto kern = int8_gemm_kernel<ACT>;
+    const int smem = (int)(p.stages * (p.a_bytes + p.b_bytes) + 1024);
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_set = smem;
+    }
+    dim3 grid((unsigned)((N + kOTileN - 1) / kOTileN), (unsigned)((M + mb - 1) / mb));
+    kern<<<grid, kOThreads, smem, st>>>(tmap_w, tmap_x, x, qw, cw, cx, jlist, jcount, bias, y, p);
+    return cuda_status(cudaGetLastError());
+}
+
+}  // namespace quanta
+
+using namespace quanta;
+
+extern "C" int quanta_int8_outlier_matmul(const void* x, int act_dtype, const int8_t* qw, const float* cw, float threshold,
+                                          const void* bias, void* y, int64_t M, int64_t N, int64_t K, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    if (!x || !qw || !cw || !y || !workspace || M <= 0 || N <= 0 || K <= 0) return QUANTA_EINVAL;
+    if (K % 16 != 0) return QUANTA_EUNSUPPORTED;                                          // TMA row pitch
+    if ((reinterpret_cast<uintptr_t>(qw) & 15) != 0) return QUANTA_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == QUANTA_BF16)
+        return outlier_launch<__nv_bfloat16>((const __nv_bfloat16*)x, qw, cw, threshold, (const __nv_bfloat16*)bias,
+                                             (__nv_bfloat16*)y, M, N, K, workspace, workspace_bytes, st);
+    if (act_dtype == QUANTA_F16)
+        return outlier_launch<__half>((const __half*)x, qw, cw, threshold, (const __half*)bias, (__half*)y, M, N, K,
+                                      workspace, workspace_bytes, st);
+    return QUANTA_EINVAL;
+}

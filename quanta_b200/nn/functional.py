@@ -41,3 +41,52 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
                                           y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
     _lib.check(st, "quanta_gemm_wna16")
     return y.reshape(*x.shape[:-1], N)
+
+
+def rowwise_quantize_sym(weight):
+    """Static int8 weight codes for the outlier-split matmul: convention-B
+    symmetric 8-bit with one multiplier per OUTPUT row, i.e.
+    ``quantize_8bit_cuda(w.t(), per_channel=True, symmetric=True)``
+    (Quanta/backends/cpu/quantization.py:29-50) transposed back and re-centred.
+    Returns (qw int8 [N, K] = code - 128, cw float32 [N] = 127 / absmax)."""
+    from ..backends.cuda.quantization import quantize_8bit_cuda
+    _host.require_cuda(weight, "weight")
+    q, scale, _ = quantize_8bit_cuda(weight.detach().float().t().contiguous(), True, True)
+    qw = (q.t().to(torch.int16) - 128).to(torch.int8).contiguous()
+    return qw, scale.reshape(-1).contiguous()
+
+
+def int8_outlier_matmul(x, qw, cw, threshold=6.0, bias=None):
+    """LLM.int8()-style y = x @ W.T + bias over int8 weight codes (row G3):
+    feature columns of ``x`` whose absolute maximum exceeds ``threshold`` go
+    through a 16-bit product with the dequantized weight columns, the rest
+    through int8 x int8 -> int32 on the tensor cores with row-wise absmax
+    scales for ``x`` (semantics: oracle/oracle_np.py:int8_outlier_matmul).
+
+    x [..., K] float16 / bfloat16; qw int8 [N, K]; cw float32 [N]."""
+    _host.require_cuda(x, "x")
+    if x.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("x must be float16 or bfloat16")
+    if qw.dtype != torch.int8 or qw.dim() != 2:
+        raise TypeError("qw must be an int8 [N, K] tensor")
+    N, K = qw.shape
+    if x.shape[-1] != K:
+        raise ValueError(f"x has {x.shape[-1]} features, weight expects {K}")
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    dev = x.device
+    y = torch.empty((M, N), dtype=x.dtype, device=dev)
+    if M == 0:
+        return y.reshape(*x.shape[:-1], N)
+    if bias is not None:
+        bias = bias.to(device=dev, dtype=x.dtype).contiguous()
+    with torch.cuda.device(dev):
+        ws = _host.workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_INT8_OUTLIER, M, K))
+        st = _lib.lib().quanta_int8_outlier_matmul(x2.data_ptr(), _host.dtype_code(x2), qw.data_ptr(), cw.data_ptr(),
+                                                   float(threshold), bias.data_ptr() if bias is not None else None,
+                                                   y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(),
+                                                   _host.stream_ptr(dev))
+    _lib.check(st, "quanta_int8_outlier_matmul")
+    return y.reshape(*x.shape[:-1], N)

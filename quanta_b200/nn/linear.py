@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from ..functional.quantization import quantize_4bit, quantize_8bit, dequantize_4bit, dequantize_8bit
-from .functional import linear_wna16
+from .functional import linear_wna16, int8_outlier_matmul, rowwise_quantize_sym
 
 
 class _QuantLinearBase(nn.Module):
@@ -100,18 +100,50 @@ class _QuantLinearBase(nn.Module):
 
 
 class Linear8bitLt(_QuantLinearBase):
-    """8-bit quantized linear layer (Quanta/nn/linear.py:10-45)."""
+    """8-bit quantized linear layer (Quanta/nn/linear.py:10-45).
+
+    ``outlier_split=False`` (default): blockwise W8A16 dequant-GEMM (row G2).
+    ``outlier_split=True``: the LLM.int8() decomposition the reference's
+    ``threshold`` argument points at (row G3) — row-wise symmetric int8 weight
+    codes, int8 x int8 tensor-core product for the regular feature columns and
+    a 16-bit product for the columns whose activations exceed ``threshold``."""
     bits = 8
 
-    def __init__(self, in_features, out_features, bias=True, has_fp16_weights=False, threshold=6.0, blocksize=64):
+    def __init__(self, in_features, out_features, bias=True, has_fp16_weights=False, threshold=6.0, blocksize=64,
+                 outlier_split=False):
         super().__init__()
         self.threshold = threshold
         self.has_fp16_weights = has_fp16_weights
+        self.outlier_split = outlier_split
         self._init_common(in_features, out_features, bias, blocksize)
+        self.register_buffer("qweight_rowwise", None, persistent=True)
+        self.register_buffer("row_scale", None, persistent=True)
+
+    @torch.no_grad()
+    def quantize_(self):
+        if not self.outlier_split:
+            return super().quantize_()
+        w = self.weight.detach()
+        self.qweight_rowwise, self.row_scale = rowwise_quantize_sym(w)
+        self.weight = nn.Parameter(torch.empty(0, device=w.device), requires_grad=False)
+        return self
+
+    def dequantize_weight(self, dtype=torch.float32):
+        if not self.outlier_split:
+            return super().dequantize_weight(dtype)
+        return (self.qweight_rowwise.float() / self.row_scale[:, None]).to(dtype)
 
     def forward(self, x):
         dt = x.dtype if x.dtype in (torch.float16, torch.bfloat16) else torch.float16
-        return self._forward_quantized(x, dt)
+        if not self.outlier_split:
+            return self._forward_quantized(x, dt)
+        if self.qweight_rowwise is None:
+            if not self.weight.is_cuda:
+                raise RuntimeError("quanta_b200 layers run on CUDA only: move the module to a GPU first")
+            self.quantize_()
+        xin = x if x.dtype == dt else x.to(dt)
+        y = int8_outlier_matmul(xin, self.qweight_rowwise, self.row_scale, self.threshold, self.bias)
+        return y if y.dtype == x.dtype or not x.is_floating_point() else y.to(x.dtype)
 
 
 class Linear4bit(_QuantLinearBase):
