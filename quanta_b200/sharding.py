@@ -1,0 +1,110 @@
+"""Row sharding of weight matrices over the GPUs of one box.
+
+Quantize / dequantize / pack need no communication: ``W[out, in]`` is cut
+along ``out`` and every rank quantizes its own rows — blockwise-64 blocks run
+along ``in`` and never straddle a row, so the shards' codes, packed bytes and
+scales are exactly the corresponding slices of the unsharded result.
+
+The tensor-parallel linear is column-parallel: rank r holds the quantized rows
+``[r0, r1)`` of W, computes ``y_r[M, r1-r0] = x @ dequant(W_r).T + b_r`` with the
+same fused kernel, and ONE all-gather (NCCL over NVLink on the GPU box, gloo
+in the CPU tests) assembles ``y[M, out]`` — the only exchange step on the path.
+One process per GPU; ``torch.distributed`` is plumbing only.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def row_shard(n_rows, world_size, rank, multiple=1):
+    """Rows ``[start, stop)`` of rank ``rank``: contiguous, sizes differ by at most
+    ``multiple`` rows, every boundary a multiple of ``multiple`` (128 keeps GEMM
+    tiles whole)."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    units = -(-n_rows // multiple)
+    base, extra = divmod(units, world_size)
+    u0 = rank * base + min(rank, extra)
+    u1 = u0 + base + (1 if rank < extra else 0)
+    return min(u0 * multiple, n_rows), min(u1 * multiple, n_rows)
+
+
+def shard_rows(weight, world_size, rank, multiple=1):
+    """This rank's contiguous row slice of ``weight[out, in]`` (a view)."""
+    r0, r1 = row_shard(weight.shape[0], world_size, rank, multiple)
+    return weight[r0:r1]
+
+
+def gather_columns(y_local, out_features, group=None, multiple=1):
+    """All-gather the column shards ``y_local[M, r1-r0]`` of every rank into
+    ``y[M, out_features]``.  Shards may differ in width (``row_shard``): they are
+    padded to the widest one for the collective and trimmed afterwards."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return y_local
+    M = y_local.shape[0]
+    bounds = [row_shard(out_features, world, r, multiple) for r in range(world)]
+    width = max(b - a for a, b in bounds)
+    send = y_local
+    if send.shape[1] != width:
+        send = torch.zeros((M, width), dtype=y_local.dtype, device=y_local.device)
+        send[:, : y_local.shape[1]] = y_local
+    recv = torch.empty((world * M, width), dtype=y_local.dtype, device=y_local.device)      # rank-major concatenation
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    recv = recv.view(world, M, width)
+    y = torch.empty((M, out_features), dtype=y_local.dtype, device=y_local.device)
+    for r, (a, b) in enumerate(bounds):
+        y[:, a:b] = recv[r, :, : b - a]
+    return y
+
+
+class TensorParallelLinear(nn.Module):
+    """Column-parallel quantized linear over ``group``: this rank holds rows
+    ``row_shard(out_features, world, rank, 128)`` of the weight, quantized
+    blockwise along ``in_features`` (convention A), and ``forward`` all-gathers
+    the ranks' output columns.  ``bits`` = 4 (packed) or 8."""
+
+    def __init__(self, in_features, out_features, bits=4, bias=True, compute_dtype=torch.bfloat16, blocksize=64,
+                 group=None):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.bits, self.blocksize, self.compute_dtype, self.group = bits, blocksize, compute_dtype, group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rows = row_shard(out_features, self.world_size, self.rank, 128)
+        self.register_buffer("qweight", None)
+        self.register_buffer("scale", None)
+        self.register_buffer("zero_point", None)
+        self.register_buffer("bias", None)
+        self._has_bias = bias
+
+    @torch.no_grad()
+    def load_shard(self, weight_rows, bias_rows=None):
+        """Quantize this rank's rows (a CUDA tensor [r1-r0, in_features]); no communication."""
+        from .functional.quantization import quantize_4bit, quantize_8bit
+        r0, r1 = self.rows
+        if tuple(weight_rows.shape) != (r1 - r0, self.in_features):
+            raise ValueError(f"expected rows {r0}:{r1} of the weight, got shape {tuple(weight_rows.shape)}")
+        if self.bits == 4:
+            self.qweight, self.scale, self.zero_point = quantize_4bit(weight_rows, blocksize=self.blocksize, packed=True)
+        else:
+            self.qweight, self.scale, self.zero_point = quantize_8bit(weight_rows, blocksize=self.blocksize)
+        if self._has_bias and bias_rows is not None:
+            self.bias = bias_rows.detach().to(self.compute_dtype).clone()
+        return self
+
+    def local_matmul(self, x):
+        """This rank's output columns ``y[:, r0:r1]`` — the fused dequant-GEMM kernel."""
+        from .nn.functional import linear_wna16
+        r0, r1 = self.rows
+        return linear_wna16(x, self.qweight, self.scale, self.zero_point, self.bias, bits=self.bits,
+                            blocksize=self.blocksize, out_features=r1 - r0, in_features=self.in_features)
+
+    def forward(self, x):
+        xin = x if x.dtype == self.compute_dtype else x.to(self.compute_dtype)
+        lead = xin.shape[:-1]
+        y_local = self.local_matmul(xin.reshape(-1, self.in_features))
+        y = gather_columns(y_local, self.out_features, self.group, 128)
+        return y.reshape(*lead, self.out_features)
