@@ -190,6 +190,7 @@ struct GemmParams {
     unsigned int U;         // work units: tiles * S  (U * G < 2^32, checked on the host)
     int nbuf;               // accumulator buffers in TMEM (1 or 2)
     int nacc;               // independent accumulators per buffer (power of 2): consecutive MMAs rotate over them
+    int nmma;               // MMA-issuing warps (2 when nacc >= 2: tcgen05.mma dispatch is per-warp bound)
     int raw_stages, x_stages;
     int xkb;                // 64-K blocks per activation slot: 4, 2 or 1 (slot <= 32 KB)
     uint32_t raw_bytes, x_kb_bytes, x_slot_bytes, x_ring_off;
@@ -244,6 +245,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 template <typename ACT, int BITS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                  const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_z,
                   const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
                   ACT* __restrict__ y, unsigned int* __restrict__ counters, float* __restrict__ partial,
                   const __grid_constant__ GemmParams p) {
@@ -284,10 +286,12 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // operands stay in uniform registers.
     if (warp == 0) {
         // ===== raw weight codes: deep TMA ring (bytes in flight hide the HBM latency) =====
+        constexpr uint32_t kRawCodeBytes = BITS == 4 ? 16384u : 32768u;
         if (lane == 0) {
             for (int s = 0; s < p.raw_stages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kDqGroupWarps); }
             fence_barrier_init();
             prefetch_tensormap(&tmap_w);
+            if (p.vec4) { prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z); }
         }
         __syncwarp();
         asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
@@ -307,6 +311,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         tma_load_2d_plain(r_addr(slot), &tmap_w, bar, s * 256, n0, pol_w);
                         tma_load_2d_plain(r_addr(slot) + 16384u, &tmap_w, bar, s * 256 + 128, n0, pol_w);
                     }
+                    if (p.vec4) {
+                        // the stage's scales and zero-points ride on the same barrier: [128 rows x 4 floats] each
+                        tma_load_2d_plain(r_addr(slot) + kRawCodeBytes, &tmap_s, bar, s * kKbPerStage, n0, pol_w);
+                        tma_load_2d_plain(r_addr(slot) + kRawCodeBytes + 2048u, &tmap_z, bar, s * kKbPerStage, n0, pol_w);
+                    }
                     TRACE(0);
                 }
                 __syncwarp();
@@ -317,7 +326,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     } else if (warp == 1) {
         // ===== activation tiles: xkb 64-K blocks per slot =====
         if (lane == 0) {
-            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], p.xkb == 4 ? p.nmma : 1); }
             fence_barrier_init();
             prefetch_tensormap(&tmap_x);
         }
@@ -348,8 +357,8 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (warp == 2) {
             tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
         } else if (warp == 3 && lane == 0) {
-            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], kDqGroupWarps); mbar_init(&a_empty[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], kEpiWarps); }
+            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], kDqGroupWarps); mbar_init(&a_empty[s], p.nmma); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], p.nmma); mbar_init(&d_empty[s], kEpiWarps); }
             fence_barrier_init();
         }
         tc_fence_before();
@@ -358,60 +367,63 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (warp == 2) {
-        // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =====
+    if (warp == 2 || (warp == 3 && p.nmma == 2)) {
+        // ===== MMA issuers: the whole warp walks the schedule, one elected lane issues =====
+        // A tcgen05.mma costs its issuing warp ~70 cycles of dispatch whatever its size while the
+        // tensor pipe itself needs only N/2 cycles, so for small batches two warps issue: warp 2 the
+        // first two 64-K blocks of every stage, warp 3 the last two, each into its own half of the
+        // rotating accumulators (the epilogue adds all of them up).
+        const int mw = warp - 2;
         const uint32_t idesc = (1u << 4) | (AT::kFmt << 7) | (AT::kFmt << 10) |
                                ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
         const uint32_t kb_desc = p.x_kb_bytes >> 4;          // descriptor step between 64-K blocks of one slot
+        const uint32_t my_acc = (uint32_t)(p.nacc / p.nmma);          // accumulators of this warp (power of 2)
         int sx = 0, seg = 0, sc = 0;
         uint32_t px = 0;
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
             const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);      // how often `buf` was used before
-            mbar_wait_warp(&d_empty[buf], (use & 1) ^ 1, lane);      // epilogue has drained this accumulator
-            // A dependent tcgen05.mma (same accumulator) costs ~100 cycles whatever its size, so the
-            // 16 MMAs of a stage rotate over `nacc` accumulators that the epilogue adds up.
-            const uint32_t tmem_d = tmem + kDBase + (uint32_t)(buf * p.nacc * p.mb);
-            uint32_t touched = 0;                            // accumulators already written in this segment
+            mbar_wait(&d_empty[buf], (use & 1) ^ 1);         // epilogue has drained this accumulator
+            const uint32_t tmem_d = tmem + kDBase + (uint32_t)((buf * p.nacc + mw * (int)my_acc) * p.mb);
+            uint32_t touched = 0;                            // own accumulators already written in this segment
             for (int s = s0; s < s1; ++s, ++sc) {
                 const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
                 const int g = sc & 1;                        // dequant group = A buffer
-                TRACE2(1, lane == 0 && sc == 0);
-                mbar_wait_warp(&a_full[g], (uint32_t)(sc >> 1) & 1u, lane);   // the stage's 4 A tiles are in TMEM
+                mbar_wait(&a_full[g], (uint32_t)(sc >> 1) & 1u);      // the stage's 4 A tiles are in TMEM
                 const uint32_t ta = tmem + (uint32_t)(g * kKbPerStage * kACols);
-                TRACE2(1, lane == 0 && sc == 0);
 #pragma unroll
                 for (int j = 0; j < kKbPerStage; ++j) {
                     const int jj = j & (p.xkb - 1);
-                    if (jj == 0) mbar_wait_warp(&x_full[sx], px, lane);   // activation slot landed
-                    TRACE2(1, lane == 0 && sc == 0);
-                    tc_fence_after();
-                    TRACE2(1, lane == 0 && sc == 0);
-                    const bool live = j < nkb && !(p.dbg & 1);
-                    uint32_t acc_idx[4], acc_flag[4];        // computed by every lane: stays warp-uniform
+                    const bool mine = p.nmma == 1 || (j >> 1) == mw;
+                    if (mine) {
+                        if (jj == 0 || (p.nmma == 2 && (j & 1) == 0)) mbar_wait(&x_full[sx], px);   // activation slot landed
+                        tc_fence_after();
+                        const bool live = j < nkb && !(p.dbg & 1);
+                        uint32_t acc_idx[4], acc_flag[4];    // computed by every lane: stays warp-uniform
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        acc_idx[k] = (uint32_t)(4 * j + k) & (uint32_t)(p.nacc - 1);
-                        acc_flag[k] = (touched >> acc_idx[k]) & 1u;
-                        if (live) touched |= 1u << acc_idx[k];
-                    }
-                    if (elect_one()) {
-                        if (live) {
-                            const uint64_t db = smem_desc_sw128(x_addr(sx)) + (uint64_t)(jj * kb_desc);
-#pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k)        // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
-                                umma_f16_ts(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
-                                            db + 2 * k, idesc, acc_flag[k]);
+                        for (int k = 0; k < 4; ++k) {
+                            acc_idx[k] = (uint32_t)(4 * j + k) & (my_acc - 1u);
+                            acc_flag[k] = (touched >> acc_idx[k]) & 1u;
+                            if (live) touched |= 1u << acc_idx[k];
                         }
-                        TRACE2(1, sc == 0);
-                        if (jj == p.xkb - 1) umma_commit(&x_empty[sx]);   // arrives when the MMAs above have read the slot
-                        if (j == kKbPerStage - 1) umma_commit(&a_empty[g]);
-                        TRACE2(1, sc == 0);
+                        if (elect_one()) {
+                            if (live) {
+                                const uint64_t db = smem_desc_sw128(x_addr(sx)) + (uint64_t)(jj * kb_desc);
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)    // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
+                                    umma_f16_ts(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
+                                                db + 2 * k, idesc, acc_flag[k]);
+                            }
+                            // both arrive when the MMAs above have read their operands; with two issuers a
+                            // slot shared by both (xkb = 4) and the A buffer need both warps' commits
+                            const bool last_of_slot = jj == p.xkb - 1 || (p.nmma == 2 && p.xkb == 4 && j == 1);
+                            if (last_of_slot) umma_commit(&x_empty[sx]);
+                            if (j == kKbPerStage - 1 || (p.nmma == 2 && j == 1)) umma_commit(&a_empty[g]);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     if (jj == p.xkb - 1) { if (++sx == p.x_stages) { sx = 0; px ^= 1; } }
                 }
-                TRACE2(1, lane == 0 && sc == 0);
             }
             if (elect_one()) umma_commit(&d_full[buf]);
             __syncwarp();
@@ -440,19 +452,26 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             mbar_wait_warp(&d_full[buf], use & 1, lane);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + kDBase + (uint32_t)(buf * p.nacc * p.mb);
-            // accumulators the MMA warp wrote in this segment: 4 per 64-K block, rotating over nacc
-            const int seg_kb = min(s1 * kKbPerStage, p.total_kb) - s0 * kKbPerStage;
-            const int nv = min(p.nacc, 4 * seg_kb);
+            // accumulators the MMA warps wrote in this segment: each warp issues 4 MMAs per 64-K block of
+            // its half of the stage (all of it with one issuer), rotating over its own my_acc accumulators
+            const int my_acc = p.nacc / p.nmma;
+            const int last_nkb = (s1 == p.S) ? p.total_kb - (p.S - 1) * kKbPerStage : kKbPerStage;
+            int kb_w[2];
+            if (p.nmma == 1) { kb_w[0] = (s1 - s0 - 1) * kKbPerStage + last_nkb; kb_w[1] = 0; }
+            else { kb_w[0] = (s1 - s0 - 1) * 2 + min(last_nkb, 2); kb_w[1] = (s1 - s0 - 1) * 2 + max(last_nkb - 2, 0); }
             for (int c0 = 0; c0 < p.mb; c0 += 16) {
                 uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
-                for (int a = 1; a < nv; ++a) {
-                    uint32_t t[16];
-                    tmem_ld16(taddr + (uint32_t)(a * p.mb) + c0, t);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+                for (int w = 0; w < p.nmma; ++w) {
+                    const int nv = min(my_acc, 4 * kb_w[w]);
+                    for (int a = 0; a < nv; ++a) {
+                        uint32_t t[16];
+                        tmem_ld16(taddr + (uint32_t)((w * my_acc + a) * p.mb) + c0, t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+                    }
                 }
                 if (c0 < m_valid) {
 #pragma unroll
@@ -494,24 +513,25 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? AT::to_float(bias[gn4 + e]) : 0.0f;
                     const size_t slot_elems = (size_t)(kTileN * p.mb);
                     const bool vec_ok = (p.N & 3) == 0 && gn4 + 3 < p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
-                    for (int mb0 = mq; mb0 < m_valid; mb0 += 16) {
-                        float4 acc[4];
+                    for (int mb0 = mq; mb0 < m_valid; mb0 += 32) {
+                        float4 acc[8];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int c = c_first; c <= c_last; ++c) {
                             const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / (unsigned int)p.S)) ? 0 : 1;
                             const float* src = partial + ((size_t)c * 2 + wc) * slot_elems + f4;
+                            float4 v[8];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
+                            for (int i = 0; i < 8; ++i) {
                                 const int m = mb0 + 4 * i;
-                                if (m < m_valid) {
-                                    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + m * kTileN));
-                                    acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
-                                }
+                                v[i] = (m < m_valid) ? __ldcg(reinterpret_cast<const float4*>(src + m * kTileN))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                             }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
                         }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 8; ++i) {
                             const int m = mb0 + 4 * i;
                             if (m < m_valid) {
                                 ACT* dst = y + (int64_t)(m0 + m) * p.N + gn4;
@@ -543,7 +563,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // this group's A buffer: 4 tiles of 32 columns; this thread's half tile starts 16 columns in
         const uint32_t a_addr = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(group * kKbPerStage * kACols + 16 * half);
         const V2 c2 = AT::dup(AT::kCentre);
-        // scale / zero-point of the group's next stage, loaded one stage of work ahead
+        // Scale / zero-point of a stage: delivered by TMA next to the raw codes (vec4), else loaded
+        // with plain loads one stage of work ahead (odd shapes: K not a multiple of 256, block > 64).
+        constexpr uint32_t kRawCodeBytes = BITS == 4 ? 16384u : 32768u;
         SegWalk ahead = walk;
         int a_tile = 0, a_s = 0, a_s1 = 0;
         bool a_ok = ahead.next(a_tile, a_s, a_s1);
@@ -552,18 +574,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const int gn = (t % p.n_tiles) * kTileN + row;
             const int64_t rbase = (int64_t)(gn < p.N ? gn : p.N - 1) * p.scale_stride;
             const int kb = s * kKbPerStage;
-            if (p.vec4) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(scale + rbase + kb));
-                const float4 c = __ldg(reinterpret_cast<const float4*>(zp + rbase + kb));
-                sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
-                zv[0] = c.x; zv[1] = c.y; zv[2] = c.z; zv[3] = c.w;
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = min(kb + j, p.total_kb - 1) >> p.block_shift;
-                    sv[j] = __ldg(scale + rbase + col);
-                    zv[j] = __ldg(zp + rbase + col);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int col = min(kb + j, p.total_kb - 1) >> p.block_shift;
+                sv[j] = __ldg(scale + rbase + col);
+                zv[j] = __ldg(zp + rbase + col);
             }
         };
         // advance `ahead` by n stages (across segments)
@@ -574,8 +589,10 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 else { n -= room; a_ok = ahead.next(a_tile, a_s, a_s1); }
             }
         };
-        skip(group);
-        if (a_ok) fetch_params(a_tile, a_s);
+        if (!p.vec4) {
+            skip(group);
+            if (a_ok) fetch_params(a_tile, a_s);
+        }
 
         int sc = 0;                 // global stage counter of this CTA
         int rslot = 0;
@@ -585,20 +602,28 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 if ((sc & (kDqGroups - 1)) == group) {
                     const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
                     float cs[4], cz[4];
+                    if (!p.vec4) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { cs[j] = sv[j]; cz[j] = zv[j]; }
-                    if (cs[0] == 12345.0f) TRACE(2 + 3 * group);   // forces the parameter loads to complete here
-                    if (lane == 0 && quarter == 0 && half == 0) TRACE(2 + 3 * group);
-                    skip(kDqGroups);
-                    if (a_ok) fetch_params(a_tile, a_s);     // lands while this stage is processed
+                        for (int j = 0; j < 4; ++j) { cs[j] = sv[j]; cz[j] = zv[j]; }
+                        skip(kDqGroups);
+                        if (a_ok) fetch_params(a_tile, a_s); // lands while this stage is processed
+                    }
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
                     mbar_wait_warp(&raw_full[rslot], rph, lane);
-                    if (lane == 0 && quarter == 0 && half == 0) TRACE(2 + 3 * group);
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
+
                     const uint32_t rrow = r_addr(rslot) + (uint32_t)row * 128u;
                     const uint32_t sw = (uint32_t)(row & 7);
+                    if (p.vec4) {
+                        const uint4 a = lds128g(r_addr(rslot) + kRawCodeBytes + (uint32_t)row * 16u);
+                        const uint4 c = lds128g(r_addr(rslot) + kRawCodeBytes + 2048u + (uint32_t)row * 16u);
+                        cs[0] = __uint_as_float(a.x); cs[1] = __uint_as_float(a.y); cs[2] = __uint_as_float(a.z); cs[3] = __uint_as_float(a.w);
+                        cz[0] = __uint_as_float(c.x); cz[1] = __uint_as_float(c.y); cz[2] = __uint_as_float(c.z); cz[3] = __uint_as_float(c.w);
+                    }
                     // the MMAs that read this group's A buffer two stages ago are done
                     mbar_wait_warp(&a_empty[group], ((uint32_t)(sc >> 1) & 1u) ^ 1u, lane);
                     tc_fence_after();
-                    if (lane == 0 && quarter == 0 && half == 0) TRACE(3 + 3 * group);
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
 #pragma unroll
                     for (int j = 0; j < kKbPerStage; ++j) {
                         if (j < nkb && !(p.dbg & 2)) {
@@ -625,15 +650,17 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             }
                             tmem_st16(a_addr + (uint32_t)(j * kACols), out);
                         }
+                        TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
                     }
                     tmem_st_wait();
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(&a_full[group]);
                         mbar_arrive(&raw_empty[rslot]);
                     }
-                    if (lane == 0 && quarter == 0 && half == 0) TRACE(4 + 3 * group);
+
                 }
                 if (++rslot == p.raw_stages) { rslot = 0; rph ^= 1; }
             }
@@ -680,7 +707,7 @@ static int choose_ctas(int tiles, int S, int mb, int raw_bytes) {
         double cost = (double)((U + G - 1) / G) * stage;
         if (G != tiles) {
             const double contributors = (double)G / tiles < 2.0 ? 2.0 : (double)G / tiles + 1.0;
-            cost += 4000.0 + tile_io * (1.0 + contributors);
+            cost += 4000.0 + 2.0 * tile_io * (1.0 + contributors);      // the last arriver's reads are latency-bound
         }
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
     };
@@ -712,6 +739,8 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     // accumulators: nbuf x nacc x mb <= 256 TMEM columns
     p.nacc = mb <= 16 ? 8 : (mb <= 64 ? 4 : (mb <= 128 ? 2 : 1));
     p.nbuf = (2 * p.nacc * mb <= kTmemCols - kDBase) ? 2 : 1;
+    p.nmma = p.nacc >= 2 ? 2 : 1;
+    if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 1) p.nmma = 1; }
     p.dbg = 0;
     if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
     p.scale_stride = (int)(K / block);
@@ -722,7 +751,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     p.x_kb_bytes = (uint32_t)mb * 128u;
     p.xkb = mb <= 64 ? 4 : (mb <= 128 ? 2 : 1);              // activation slots of at most 32 KB
     p.x_slot_bytes = p.x_kb_bytes * (uint32_t)p.xkb;
-    p.raw_bytes = BITS == 4 ? 16384u : 32768u;
+    p.raw_bytes = (BITS == 4 ? 16384u : 32768u) + (p.vec4 ? 4096u : 0u);    // codes (+ scale / zero-point tiles)
     // Shared-memory budget: an activation ring sized for the MMA, everything else for the raw-code
     // ring — raw bytes in flight are what hides the HBM latency.
     const uint32_t budget = 214u * 1024u;
@@ -750,6 +779,15 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
                             (uint32_t)mb, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
+    CUtensorMap tmap_s = tmap_w, tmap_z = tmap_w;          // placeholders unless the parameters ride on TMA
+    if (p.vec4) {
+        rc = make_tensor_map_2d(&tmap_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, scale, (uint64_t)p.scale_stride, (uint64_t)N,
+                                (uint64_t)p.scale_stride * 4, kKbPerStage, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        rc = make_tensor_map_2d(&tmap_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zp, (uint64_t)p.scale_stride, (uint64_t)N,
+                                (uint64_t)p.scale_stride * 4, kKbPerStage, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
     auto kern = gemm_wna16_kernel<ACT, BITS>;
     const int smem = (int)(p.x_ring_off + (uint32_t)p.x_stages * p.x_slot_bytes + 1024);
     static int smem_set = 0;           // per instantiation
@@ -758,7 +796,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    kern<<<p.G, kGemmThreads, smem, st>>>(tmap_w, tmap_x, scale, zp, bias, y, counters, partial, p);
+    kern<<<p.G, kGemmThreads, smem, st>>>(tmap_w, tmap_x, tmap_s, tmap_z, scale, zp, bias, y, counters, partial, p);
     return cuda_status(cudaGetLastError());
 }
 
