@@ -197,6 +197,7 @@ struct GemmParams {
     int scale_stride;       // K / block
     int block_shift;        // log2(block / 64)
     int vec4;               // scale / zero-point rows can be read as float4 per stage
+    int y_tma;              // whole tiles leave through a TMA store (needs N % 8 == 0 and an aligned y)
     int dbg;                // experiment switches (QUANTA_B200_GEMM_DBG): 1 = no MMA, 2 = no dequant math/store
 };
 
@@ -238,15 +239,87 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int) {
-    mbar_wait(bar, parity);          // measured: every lane polling beats one lane + reconvergence
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------
+// In a cluster the shared-window address of a CTA carries its rank in bit 24; clearing it names
+// the same offset in the even (leader) CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// arrive on the leader CTA's copy of `bar` (a local arrive when this CTA is the leader)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// wait with cluster-scope acquire: the barrier is completed by the peer CTA's arrivals / TMA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <int CG> __device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity) {
+    if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+}
+template <int CG> __device__ __forceinline__ void tmem_alloc_cg(uint32_t smem_dst, uint32_t ncols) {
+    if (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        tmem_alloc(smem_dst, ncols);
+    }
+}
+template <int CG> __device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else tmem_dealloc(taddr, ncols);
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_ts_cg(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 2) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        umma_f16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+    }
+}
+// completes `bar` in this CTA (CG = 1) or at the same offset in both CTAs of the pair (CG = 2)
+template <int CG> __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+    if (CG == 2) {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    } else {
+        umma_commit(bar);
+    }
+}
+// activation tile load; in a pair both CTAs signal the leader's barrier
+template <int CG>
+__device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, uint64_t policy) {
+    if (CG == 2) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+            : "memory");
+    } else {
+        tma_load_2d_plain(dst, map, bar, c0, c1, policy);
+    }
 }
 
-template <typename ACT, int BITS>
+template <typename ACT, int BITS, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_z,
-                  const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tmap_y, const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
                   ACT* __restrict__ y, unsigned int* __restrict__ counters, float* __restrict__ partial,
                   const __grid_constant__ GemmParams p) {
     using AT = ActTraits<ACT>;
@@ -255,6 +328,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     __shared__ uint64_t a_full[kDqGroups], a_empty[kDqGroups], d_full[2], d_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int fix_flag;
+    __shared__ __align__(1024) float stage[16][kTileN];        // epilogue transpose buffer (8 KB)
 #ifdef QUANTA_GEMM_TRACE
     __shared__ long long trace[8][48];
     const bool tr = (p.dbg & 8) && blockIdx.x == 0;
@@ -270,7 +344,12 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
-    const unsigned int cta = blockIdx.x;
+    // CG = 2: the two CTAs of a cluster form a pair (tcgen05 cta_group::2): they walk the same unit
+    // range on adjacent 128-feature tiles, each loads half of the activation rows, and the leader
+    // (rank 0) issues one 256-feature MMA for both.  `cta` is the scheduling unit (CTA or pair).
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
+    const unsigned int cta = blockIdx.x / CG;
 
     // shared memory: [raw ring: raw_stages x 16|32 KB][x ring: x_stages x (xkb x mb x 128 B)]
     auto r_addr = [&](int s) { return smem + (uint32_t)s * p.raw_bytes; };
@@ -294,12 +373,13 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             if (p.vec4) { prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z); }
         }
         __syncwarp();
-        asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
+        if (CG == 2) cluster_arrive();                       // checked in; the matching wait comes after the stream
+        else asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
         const uint64_t pol_w = policy_evict_first();         // weights are streamed once
         int slot = 0, issued = 0;
         uint32_t ph = 0;
         while (walk.next(tile, s0, s1)) {
-            const int n0 = (tile % p.n_tiles) * kTileN;
+            const int n0 = ((tile % p.n_tiles) * CG + (int)crank) * kTileN;
             for (int s = s0; s < s1; ++s) {
                 if (issued >= p.raw_stages) mbar_wait(&raw_empty[slot], ph ^ 1);
                 if (elect_one()) {
@@ -323,6 +403,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 if (++slot == p.raw_stages) { slot = 0; ph ^= 1; }
             }
         }
+        if (CG == 2) cluster_wait();
     } else if (warp == 1) {
         // ===== activation tiles: xkb 64-K blocks per slot =====
         if (lane == 0) {
@@ -331,23 +412,25 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             prefetch_tensormap(&tmap_x);
         }
         __syncwarp();
-        asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
+        if (CG == 2) { cluster_arrive(); cluster_wait(); }   // the peer's barriers must exist before the first load
+        else asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
         const uint64_t pol_x = policy_evict_last();          // activations are re-read by every CTA
         int slot = 0, issued = 0;
         uint32_t ph = 0;
         while (walk.next(tile, s0, s1)) {
-            const int m0 = (tile / p.n_tiles) * p.mb;
+            const int m0 = (tile / p.n_tiles) * p.mb + (int)crank * (p.mb / CG);     // this CTA's half of the rows
             for (int s = s0; s < s1; ++s) {
                 for (int j = 0; j < kKbPerStage; j += p.xkb) {
                     if (issued >= p.x_stages) mbar_wait(&x_empty[slot], ph ^ 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&x_full[slot], p.x_slot_bytes);
+                        if (leader) mbar_arrive_expect_tx(&x_full[slot], p.x_slot_bytes * CG);    // both halves
                         // blocks past the end of K are out of bounds and arrive zero-filled
                         for (int jj = 0; jj < p.xkb; ++jj)
-                            tma_load_2d_plain(x_addr(slot) + (uint32_t)jj * p.x_kb_bytes, &tmap_x, smem_u32(&x_full[slot]),
-                                              (s * kKbPerStage + j + jj) * kBlockK, m0, pol_x);
+                            tma_load_x<CG>(x_addr(slot) + (uint32_t)jj * p.x_kb_bytes, &tmap_x, smem_u32(&x_full[slot]),
+                                           (s * kKbPerStage + j + jj) * kBlockK, m0, pol_x);
                     }
                     __syncwarp();
+                    TRACE2(3, lane == 0);
                     ++issued;
                     if (++slot == p.x_stages) { slot = 0; ph ^= 1; }
                 }
@@ -355,19 +438,22 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     } else {
         if (warp == 2) {
-            tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+            tmem_alloc_cg<CG>(smem_u32(&tmem_base_slot), kTmemCols);
         } else if (warp == 3 && lane == 0) {
-            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], kDqGroupWarps); mbar_init(&a_empty[s], p.nmma); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], p.nmma); mbar_init(&d_empty[s], kEpiWarps); }
+            // a_full / d_empty live in the leader and collect both CTAs' arrivals
+            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], CG * kDqGroupWarps); mbar_init(&a_empty[s], p.nmma); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], p.nmma); mbar_init(&d_empty[s], CG * kEpiWarps); }
             fence_barrier_init();
         }
+        __syncwarp();
         tc_fence_before();
-        asm volatile("barrier.sync 2, %0;" ::"n"(kGemmThreads) : "memory");
+        if (CG == 2) { cluster_arrive(); cluster_wait(); }
+        else asm volatile("barrier.sync 2, %0;" ::"n"(kGemmThreads) : "memory");
     }
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (warp == 2 || (warp == 3 && p.nmma == 2)) {
+    if (leader && (warp == 2 || (warp == 3 && p.nmma == 2))) {
         // ===== MMA issuers: the whole warp walks the schedule, one elected lane issues =====
         // A tcgen05.mma costs its issuing warp ~70 cycles of dispatch whatever its size while the
         // tensor pipe itself needs only N/2 cycles, so for small batches two warps issue: warp 2 the
@@ -375,7 +461,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // rotating accumulators (the epilogue adds all of them up).
         const int mw = warp - 2;
         const uint32_t idesc = (1u << 4) | (AT::kFmt << 7) | (AT::kFmt << 10) |
-                               ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+                               ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)((kTileN * CG) >> 4) << 24);
         const uint32_t kb_desc = p.x_kb_bytes >> 4;          // descriptor step between 64-K blocks of one slot
         const uint32_t my_acc = (uint32_t)(p.nacc / p.nmma);          // accumulators of this warp (power of 2)
         int sx = 0, seg = 0, sc = 0;
@@ -383,20 +469,21 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
             const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);      // how often `buf` was used before
-            mbar_wait(&d_empty[buf], (use & 1) ^ 1);         // epilogue has drained this accumulator
+            mbar_wait_x<CG>(&d_empty[buf], (use & 1) ^ 1);   // the epilogues have drained this accumulator
             const uint32_t tmem_d = tmem + kDBase + (uint32_t)((buf * p.nacc + mw * (int)my_acc) * p.mb);
             uint32_t touched = 0;                            // own accumulators already written in this segment
             for (int s = s0; s < s1; ++s, ++sc) {
                 const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
                 const int g = sc & 1;                        // dequant group = A buffer
-                mbar_wait(&a_full[g], (uint32_t)(sc >> 1) & 1u);      // the stage's 4 A tiles are in TMEM
+                mbar_wait_x<CG>(&a_full[g], (uint32_t)(sc >> 1) & 1u);       // the stage's 4 A tiles are in TMEM
                 const uint32_t ta = tmem + (uint32_t)(g * kKbPerStage * kACols);
+                TRACE2(2, lane == 0);
 #pragma unroll
                 for (int j = 0; j < kKbPerStage; ++j) {
                     const int jj = j & (p.xkb - 1);
                     const bool mine = p.nmma == 1 || (j >> 1) == mw;
                     if (mine) {
-                        if (jj == 0 || (p.nmma == 2 && (j & 1) == 0)) mbar_wait(&x_full[sx], px);   // activation slot landed
+                        if (jj == 0 || (p.nmma == 2 && (j & 1) == 0)) mbar_wait_x<CG>(&x_full[sx], px);    // activation slot landed
                         tc_fence_after();
                         const bool live = j < nkb && !(p.dbg & 1);
                         uint32_t acc_idx[4], acc_flag[4];    // computed by every lane: stays warp-uniform
@@ -411,21 +498,22 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                                 const uint64_t db = smem_desc_sw128(x_addr(sx)) + (uint64_t)(jj * kb_desc);
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)    // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
-                                    umma_f16_ts(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
+                                    umma_f16_ts_cg<CG>(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
                                                 db + 2 * k, idesc, acc_flag[k]);
                             }
                             // both arrive when the MMAs above have read their operands; with two issuers a
                             // slot shared by both (xkb = 4) and the A buffer need both warps' commits
                             const bool last_of_slot = jj == p.xkb - 1 || (p.nmma == 2 && p.xkb == 4 && j == 1);
-                            if (last_of_slot) umma_commit(&x_empty[sx]);
-                            if (j == kKbPerStage - 1 || (p.nmma == 2 && j == 1)) umma_commit(&a_empty[g]);
+                            if (last_of_slot) umma_commit_cg<CG>(&x_empty[sx]);
+                            if (j == kKbPerStage - 1 || (p.nmma == 2 && j == 1)) umma_commit_cg<CG>(&a_empty[g]);
                         }
                         __syncwarp();
                     }
                     if (jj == p.xkb - 1) { if (++sx == p.x_stages) { sx = 0; px ^= 1; } }
                 }
+                TRACE2(2, lane == 0);
             }
-            if (elect_one()) umma_commit(&d_full[buf]);
+            if (elect_one()) umma_commit_cg<CG>(&d_full[buf]);
             __syncwarp();
             ++seg;
         }
@@ -434,11 +522,12 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int quarter = warp & 3;
         const int row = 32 * quarter + lane;
         const int etid = tid - 32 * kFirstEpiWarp;
+        if (etid == 0 && p.y_tma) prefetch_tensormap(&tmap_y);
         int seg = 0;
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
             const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);
-            const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+            const int n_tile = (tile % p.n_tiles) * CG + (int)crank, m_tile = tile / p.n_tiles;
             const int gn = n_tile * kTileN + row, m0 = m_tile * p.mb;
             const bool n_ok = gn < p.N;
             const int m_valid = min(p.mb, p.M - m0);
@@ -447,11 +536,20 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             // this CTA's partial slot for the tile: 0 if the tile is the first one the CTA touches, else 1
             const unsigned int u_first = p.U * cta / (unsigned int)p.G;
             const int which = (tile == (int)(u_first / (unsigned int)p.S)) ? 0 : 1;
-            float* mine = partial + ((size_t)cta * 2 + which) * (size_t)(kTileN * p.mb);
+            float* mine = partial + (((size_t)cta * 2 + which) * CG + crank) * (size_t)(kTileN * p.mb);
 
-            mbar_wait_warp(&d_full[buf], use & 1, lane);
+            TRACE2(4, etid == 0);
+            mbar_wait(&d_full[buf], use & 1);
             tc_fence_after();
+            TRACE2(4, etid == 0);
             const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + kDBase + (uint32_t)(buf * p.nacc * p.mb);
+            // store mapping: thread -> 4 consecutive features (f4..f4+3), batch rows etid/32 + 4q
+            const int f4 = 4 * (etid & 31);
+            const int gn4 = n_tile * kTileN + f4;
+            float b4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? AT::to_float(bias[gn4 + e]) : 0.0f;
+            const bool vec_ok = (p.N & 3) == 0 && gn4 + 3 < p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
             // accumulators the MMA warps wrote in this segment: each warp issues 4 MMAs per 64-K block of
             // its half of the stage (all of it with one issuer), rotating over its own my_acc accumulators
             const int my_acc = p.nacc / p.nmma;
@@ -473,21 +571,62 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
                     }
                 }
+                if (whole && p.y_tma) {
+                    // Whole tile: bias, 16-bit conversion, [16 rows x 128 features] staged in shared memory
+                    // (two 4 KB buffers), then ONE TMA store per chunk; rows past M / features past N are
+                    // clipped by the tensor map.  (Plain global stores from this kernel cost ~10 cycles
+                    // per warp-store per SM: 20K cycles for a 128 x 256 tile.)
+                    ACT* sbuf = reinterpret_cast<ACT*>(&stage[0][0]) + ((c0 >> 4) & 1) * (16 * kTileN);
+                    if (etid == 0 && c0 >= 32) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store has read it
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sbuf[j * kTileN + row] = AT::from_float(__uint_as_float(r[j]) + b);
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                    if (etid == 0 && c0 < m_valid) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmap_y)), "r"(smem_u32(sbuf)), "r"(n_tile * kTileN), "r"(m0 + c0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    continue;
+                }
+                // Otherwise transpose the chunk through shared memory so that the stores are full rows:
+                // thread -> 4 consecutive features of 4 batch rows, 8 / 16 bytes per store.
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // previous chunk fully read
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stage[j][row] = __uint_as_float(r[j]);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (c0 < m_valid) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int m = c0 + j;
+                    for (int q = 0; q < 4; ++q) {
+                        const int ml = 4 * q + (etid >> 5);              // batch row within the chunk
+                        const int m = c0 + ml;
                         if (m < m_valid) {
-                            const float v = __uint_as_float(r[j]);
-                            if (whole) { if (n_ok) y[(int64_t)(m0 + m) * p.N + gn] = AT::from_float(v + b); }
-                            else mine[m * kTileN + row] = v;
+                            const float4 v = *reinterpret_cast<const float4*>(&stage[ml][f4]);
+                            if (whole) {
+                                ACT* dst = y + (int64_t)(m0 + m) * p.N + gn4;
+                                const float o[4] = {v.x + b4[0], v.y + b4[1], v.z + b4[2], v.w + b4[3]};
+                                if (vec_ok) {
+                                    uint2 pk;
+                                    pk.x = AT::pack(o[0], o[1]);
+                                    pk.y = AT::pack(o[2], o[3]);
+                                    *reinterpret_cast<uint2*>(dst) = pk;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                                }
+                            } else {
+                                *reinterpret_cast<float4*>(mine + m * kTileN + f4) = v;
+                            }
                         }
                     }
                 }
             }
+            if (whole && p.y_tma && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free for the next segment
+            TRACE2(4, etid == 0);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[buf]);       // accumulator may be overwritten
+            if (lane == 0) { if (CG == 2) mbar_arrive_leader(&d_empty[buf]); else mbar_arrive(&d_empty[buf]); }   // accumulator may be overwritten
             if (!whole) {
                 // stream-K fix-up: the CTA that arrives last at the tile's counter reduces every partial
                 const unsigned int tu0 = (unsigned int)tile * (unsigned int)p.S;
@@ -497,29 +636,24 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (etid == 0) {
                     __threadfence();
-                    const unsigned int old = atomicAdd(&counters[tile], 1u);
+                    const unsigned int old = atomicAdd(&counters[tile * CG + (int)crank], 1u);
                     __threadfence();
                     const int last = (old == (unsigned int)(c_last - c_first)) ? 1 : 0;
-                    if (last) counters[tile] = 0u;           // leave the workspace clean for the next call
+                    if (last) counters[tile * CG + (int)crank] = 0u;      // leave the workspace clean for the next call
                     fix_flag = last;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (fix_flag) {
                     // thread -> 4 consecutive features, every 4th batch row; 4 rows x all contributors in flight
-                    const int f4 = 4 * (etid & 31), mq = etid >> 5;
-                    const int gn4 = n_tile * kTileN + f4;
-                    float b4[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? AT::to_float(bias[gn4 + e]) : 0.0f;
+                    const int mq = etid >> 5;
                     const size_t slot_elems = (size_t)(kTileN * p.mb);
-                    const bool vec_ok = (p.N & 3) == 0 && gn4 + 3 < p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
                     for (int mb0 = mq; mb0 < m_valid; mb0 += 32) {
                         float4 acc[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int c = c_first; c <= c_last; ++c) {
                             const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / (unsigned int)p.S)) ? 0 : 1;
-                            const float* src = partial + ((size_t)c * 2 + wc) * slot_elems + f4;
+                            const float* src = partial + (((size_t)c * 2 + wc) * CG + crank) * slot_elems + f4;
                             float4 v[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
@@ -571,7 +705,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         bool a_ok = ahead.next(a_tile, a_s, a_s1);
         float sv[4], zv[4];
         auto fetch_params = [&](int t, int s) {
-            const int gn = (t % p.n_tiles) * kTileN + row;
+            const int gn = ((t % p.n_tiles) * CG + (int)crank) * kTileN + row;
             const int64_t rbase = (int64_t)(gn < p.N ? gn : p.N - 1) * p.scale_stride;
             const int kb = s * kKbPerStage;
 #pragma unroll
@@ -608,9 +742,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         skip(kDqGroups);
                         if (a_ok) fetch_params(a_tile, a_s); // lands while this stage is processed
                     }
-                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
-                    mbar_wait_warp(&raw_full[rslot], rph, lane);
-                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 8);
+                    mbar_wait(&raw_full[rslot], rph);
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 8);
 
                     const uint32_t rrow = r_addr(rslot) + (uint32_t)row * 128u;
                     const uint32_t sw = (uint32_t)(row & 7);
@@ -621,9 +755,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         cz[0] = __uint_as_float(c.x); cz[1] = __uint_as_float(c.y); cz[2] = __uint_as_float(c.z); cz[3] = __uint_as_float(c.w);
                     }
                     // the MMAs that read this group's A buffer two stages ago are done
-                    mbar_wait_warp(&a_empty[group], ((uint32_t)(sc >> 1) & 1u) ^ 1u, lane);
+                    mbar_wait(&a_empty[group], ((uint32_t)(sc >> 1) & 1u) ^ 1u);
                     tc_fence_after();
-                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 8);
 #pragma unroll
                     for (int j = 0; j < kKbPerStage; ++j) {
                         if (j < nkb && !(p.dbg & 2)) {
@@ -650,14 +784,14 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             }
                             tmem_st16(a_addr + (uint32_t)(j * kACols), out);
                         }
-                        TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
+                        TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 8);
                     }
                     tmem_st_wait();
-                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 6);
+                    TRACE2(1, lane == 0 && quarter == 0 && half == 0 && group == 0 && sc >= 4 && sc <= 8);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_arrive(&a_full[group]);
+                        if (CG == 2) mbar_arrive_leader(&a_full[group]); else mbar_arrive(&a_full[group]);
                         mbar_arrive(&raw_empty[rslot]);
                     }
 
@@ -667,9 +801,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     }
 
+    if (tid == 32 * kFirstEpiWarp) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // y stores have landed
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
+    if (CG == 2) { cluster_arrive(); cluster_wait(); }       // the peer may still be signalling into this CTA
+    if (warp == 2) { tc_fence_after(); tmem_dealloc_cg<CG>(tmem, kTmemCols); }
 #ifdef QUANTA_GEMM_TRACE
     if (tr && tid == 0) {
         printf("end %lld\n", clock64() - t_start);
@@ -680,82 +816,65 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
 // ---- host side --------------------------------------------------------------
 
-size_t gemm_workspace_bytes(int64_t M, int64_t N);
-size_t gemm_workspace_bytes(int64_t M, int64_t) {
-    int64_t mb = (M + 15) / 16 * 16;
-    if (mb > 256) mb = 256;
-    return (size_t)kCounterBytes + (size_t)kNumSMs * 2 * kTileN * (size_t)mb * sizeof(float) + 512;
-}
 
-// Number of CTAs: every SM with equal contiguous unit ranges (stream-K), or tiles x s CTAs whose
-// ranges coincide with tile boundaries (s = 1: no partials at all).  Costs in SM cycles, from
-// the measurements in DESIGN.md: a stage (256 K) costs the MMA warp ~600 cycles of barrier
-// traffic plus 16 MMAs of max(70, mb/2) cycles each, the dequant groups ~650 cycles, and one SM
-// pulls its raw codes and activation tiles (re-read by every tile) out of L2 at ~29 B/cycle;
-// a partial costs its fp32 store, ~4000 cycles of release/acquire latency and the last
-// arriver's reads of every contributor's tile at ~32 B/cycle.
-static int choose_ctas(int tiles, int S, int mb, int raw_bytes) {
+// Number of scheduling units (CTAs, or CTA pairs when cg = 2): every SM with equal contiguous unit
+// ranges (stream-K), or tiles x s units whose ranges coincide with tile boundaries (s = 1: no
+// partials at all).  Costs in SM cycles, from the measurements in DESIGN.md: a stage (256 K) costs
+// the MMA warp ~600 cycles of barrier traffic plus 16 MMAs of max(70, mb/2) cycles each, the
+// dequant groups ~930 cycles, and one SM pulls its raw codes and its share of the activation
+// tiles (re-read by every tile) out of L2 at ~29 B/cycle; a partial costs its fp32 store, ~4000
+// cycles of release/acquire latency and the last arriver's (latency-bound) reads of every
+// contributor's tile.
+static int choose_units(int tiles, int S, int mb, int raw_bytes, int cg) {
+    const int max_units = kNumSMs / cg;
     const long long U = (long long)tiles * S;
     const double mma = 600.0 + 16.0 * (mb / 2.0 > 70.0 ? mb / 2.0 : 70.0);
-    const double pull = (512.0 * mb + raw_bytes) / 29.0;
-    const double stage = fmax(fmax(mma, 650.0), pull);
+    const double pull = (512.0 * mb / cg + raw_bytes) / 29.0;
+    const double stage = fmax(fmax(mma, 930.0), pull);
     const double tile_io = (double)kTileN * mb * 4.0 / 32.0;
     int best = 1;
     double best_cost = -1.0;
     auto consider = [&](int G) {
-        if (G < 1 || G > kNumSMs || (long long)G > U) return;
+        if (G < 1 || G > max_units || (long long)G > U) return;
         double cost = (double)((U + G - 1) / G) * stage;
         if (G != tiles) {
             const double contributors = (double)G / tiles < 2.0 ? 2.0 : (double)G / tiles + 1.0;
-            cost += 4000.0 + 2.0 * tile_io * (1.0 + contributors);      // the last arriver's reads are latency-bound
+            cost += 4000.0 + 2.0 * tile_io * (1.0 + contributors);
         }
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
     };
-    consider(tiles <= kNumSMs ? tiles : 0);
-    for (int s = 2; tiles * s <= kNumSMs && s <= S; ++s) consider(tiles * s);
-    consider((int)(U < kNumSMs ? U : kNumSMs));
+    consider(tiles <= max_units ? tiles : 0);
+    for (int s = 2; tiles * s <= max_units && s <= S; ++s) consider(tiles * s);
+    consider((int)(U < max_units ? U : max_units));
     return best;
 }
 
-template <typename ACT, int BITS>
-static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
-                       const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                       cudaStream_t st) {
-    GemmParams p;
-    p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    int mb = (int)((M + 15) / 16 * 16);
+size_t gemm_workspace_bytes(int64_t M, int64_t N);
+size_t gemm_workspace_bytes(int64_t M, int64_t) {
+    int64_t mb = (M + 31) / 32 * 32;
     if (mb > 256) mb = 256;
-    p.mb = mb;
-    p.m_tiles = (int)((M + mb - 1) / mb);
-    p.n_tiles = (int)((N + kTileN - 1) / kTileN);
-    p.total_kb = (int)(K / kBlockK);
-    p.S = (p.total_kb + kKbPerStage - 1) / kKbPerStage;
-    const int tiles = p.n_tiles * p.m_tiles;
-    if (tiles > kMaxTiles) return QUANTA_EUNSUPPORTED;
+    return (size_t)kCounterBytes + (size_t)kNumSMs * 2 * kTileN * (size_t)mb * sizeof(float) + 512;
+}
+
+template <typename ACT, int BITS, int CG>
+static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const float* scale, const float* zp,
+                          const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
+                          cudaStream_t st) {
+    const int mb = p.mb;
+    const int tiles = p.n_tiles * p.m_tiles;               // scheduling tiles: CG adjacent 128-feature tiles each
+    if (tiles * CG > kMaxTiles) return QUANTA_EUNSUPPORTED;
     if ((unsigned long long)tiles * (unsigned long long)p.S * (unsigned long long)(kNumSMs + 1) >= (1ull << 32)) return QUANTA_EUNSUPPORTED;
     p.U = (unsigned int)tiles * (unsigned int)p.S;
-    p.G = choose_ctas(tiles, p.S, mb, BITS == 4 ? 16384 : 32768);
-    if (const char* e = getenv("QUANTA_B200_GEMM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= kNumSMs && (unsigned int)v <= p.U) p.G = v; }
-    // accumulators: nbuf x nacc x mb <= 256 TMEM columns
-    p.nacc = mb <= 16 ? 8 : (mb <= 64 ? 4 : (mb <= 128 ? 2 : 1));
-    p.nbuf = (2 * p.nacc * mb <= kTmemCols - kDBase) ? 2 : 1;
-    p.nmma = p.nacc >= 2 ? 2 : 1;
-    if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 1) p.nmma = 1; }
-    p.dbg = 0;
-    if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
-    p.scale_stride = (int)(K / block);
-    int bs = 0; while ((int64_t)(kBlockK << bs) < block) ++bs;
-    p.block_shift = bs;
-    p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
-              ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
-    p.x_kb_bytes = (uint32_t)mb * 128u;
-    p.xkb = mb <= 64 ? 4 : (mb <= 128 ? 2 : 1);              // activation slots of at most 32 KB
+    p.G = choose_units(tiles, p.S, mb, BITS == 4 ? 16384 : 32768, CG);
+    if (const char* e = getenv("QUANTA_B200_GEMM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= kNumSMs / CG && (unsigned int)v <= p.U) p.G = v; }
+    p.x_kb_bytes = (uint32_t)(mb / CG) * 128u;              // this CTA's rows of one 64-K block
+    p.xkb = p.x_kb_bytes <= 8192u ? 4 : (p.x_kb_bytes <= 16384u ? 2 : 1);    // activation slots of at most 32 KB
     p.x_slot_bytes = p.x_kb_bytes * (uint32_t)p.xkb;
     p.raw_bytes = (BITS == 4 ? 16384u : 32768u) + (p.vec4 ? 4096u : 0u);    // codes (+ scale / zero-point tiles)
     // Shared-memory budget: an activation ring sized for the MMA, everything else for the raw-code
     // ring — raw bytes in flight are what hides the HBM latency.
     const uint32_t budget = 214u * 1024u;
-    int x_stages = mb <= 16 ? 6 : (mb <= 32 ? 4 : (mb <= 64 ? 3 : 4));      // 48 / 64 / 96 / 128 KB
+    int x_stages = p.x_slot_bytes <= 8192u ? 6 : (p.x_slot_bytes <= 16384u ? 4 : (p.x_kb_bytes <= 8192u ? 3 : 4));
     int raw_stages = (int)((budget - (uint32_t)x_stages * p.x_slot_bytes) / p.raw_bytes);
     if (raw_stages > kMaxRing) raw_stages = kMaxRing;
     raw_stages &= ~1;                  // even: a raw slot is always consumed by the same dequant group
@@ -764,7 +883,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     p.x_stages = x_stages;
     p.x_ring_off = (uint32_t)raw_stages * p.raw_bytes;
 
-    const size_t need = (size_t)kCounterBytes + (size_t)p.G * 2 * kTileN * (size_t)mb * sizeof(float) + 256;
+    const size_t need = (size_t)kCounterBytes + (size_t)p.G * CG * 2 * kTileN * (size_t)mb * sizeof(float) + 256;
     if (!workspace || ws_bytes < need) return QUANTA_EWORKSPACE;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
@@ -776,7 +895,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
                                 128, kTileN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_tensor_map_2d(&tmap_x, ActTraits<ACT>::kTma, 2, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK,
-                            (uint32_t)mb, CU_TENSOR_MAP_SWIZZLE_128B);
+                            (uint32_t)(mb / CG), CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
     CUtensorMap tmap_s = tmap_w, tmap_z = tmap_w;          // placeholders unless the parameters ride on TMA
@@ -788,7 +907,15 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
                                 (uint64_t)p.scale_stride * 4, kKbPerStage, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
-    auto kern = gemm_wna16_kernel<ACT, BITS>;
+    CUtensorMap tmap_y = tmap_w;
+    p.y_tma = ((N & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
+    if (const char* e = getenv("QUANTA_B200_GEMM_YTMA")) { if (atoi(e) == 0) p.y_tma = 0; }
+    if (p.y_tma) {
+        rc = make_tensor_map_2d(&tmap_y, ActTraits<ACT>::kTma, 2, y, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, kTileN, 16,
+                                CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
+    auto kern = gemm_wna16_kernel<ACT, BITS, CG>;
     const int smem = (int)(p.x_ring_off + (uint32_t)p.x_stages * p.x_slot_bytes + 1024);
     static int smem_set = 0;           // per instantiation
     if (smem > smem_set) {             // static __shared__ (barriers) also counts against the 227 KB opt-in limit
@@ -796,8 +923,55 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    kern<<<p.G, kGemmThreads, smem, st>>>(tmap_w, tmap_x, tmap_s, tmap_z, scale, zp, bias, y, counters, partial, p);
-    return cuda_status(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.G * CG));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG == 2 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_x, tmap_s, tmap_z, tmap_y, scale, zp, bias, y, counters, partial, p);
+    return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+template <typename ACT, int BITS>
+static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
+                       const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
+                       cudaStream_t st) {
+    GemmParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    const int n_tiles = (int)((N + kTileN - 1) / kTileN);
+    // CTA pairs (tcgen05 cta_group::2: one 256-feature MMA per pair, each CTA loads half of the
+    // activation rows) are implemented and parity-tested but measured 10-25 % slower than single
+    // CTAs on the Llama shapes in round 1 (later pipeline start, tighter coupling of the two
+    // dequant pipelines), so they are opt-in: QUANTA_B200_GEMM_CG=2.
+    int cg = 1;
+    if (const char* e = getenv("QUANTA_B200_GEMM_CG")) { int v = atoi(e); if (v == 1 || (v == 2 && n_tiles >= 2)) cg = v; }
+    const int mb_step = 16 * cg;                             // each CTA of a pair holds mb / 2 rows, a multiple of 16
+    int mb = (int)((M + mb_step - 1) / mb_step * mb_step);
+    if (mb > 256) mb = 256;
+    p.mb = mb;
+    p.m_tiles = (int)((M + mb - 1) / mb);
+    p.n_tiles = (n_tiles + cg - 1) / cg;
+    p.total_kb = (int)(K / kBlockK);
+    p.S = (p.total_kb + kKbPerStage - 1) / kKbPerStage;
+    // accumulators: nbuf x nacc x mb <= 256 TMEM columns
+    p.nacc = mb <= 16 ? 8 : (mb <= 64 ? 4 : (mb <= 128 ? 2 : 1));
+    p.nbuf = (2 * p.nacc * mb <= kTmemCols - kDBase) ? 2 : 1;
+    p.nmma = 1;
+    if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 2 && p.nacc >= 2) p.nmma = 2; }
+    p.dbg = 0;
+    if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
+    p.scale_stride = (int)(K / block);
+    int bs = 0; while ((int64_t)(kBlockK << bs) < block) ++bs;
+    p.block_shift = bs;
+    p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
+              ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
+    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2>(p, x, wq, scale, zp, bias, y, M, N, K, workspace, ws_bytes, st);
+    return gemm_launch_cg<ACT, BITS, 1>(p, x, wq, scale, zp, bias, y, M, N, K, workspace, ws_bytes, st);
 }
 
 }  // namespace quanta
