@@ -16,8 +16,13 @@ A "step" is one pass over all 224 matrices.
             against the measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline  the C oracle port of the reference algorithm on the host cores
 
-`--impl reference` times the reference's CPU algorithm (oracle port; the
-reference itself is pure Python/torch and does not travel to the GPU box).
+`--impl reference` times the reference's CPU implementation of the path on the
+host cores: the reference is pure Python on eager torch ops and does not travel
+to the GPU box, so the arm runs oracle/oracle_torch.py — the same chain of
+whole-tensor torch ops (bit-identical results, tests/test_oracle_torch.py) with
+all host threads.  `cpu_baseline` of the default arm is the same measurement on
+a bounded sample; the hand-optimised C/OpenMP port of the arithmetic
+(oracle/quanta_oracle.c) is reported next to it as `c_port_value`.
 N > 1 (torchrun): every rank quantizes its own 7B-shaped weight set (weak
 scaling, no data-path collective — SURVEY §8(e)).
 """
@@ -110,6 +115,7 @@ def cpu_sample(threads=None):
 
 
 def time_cpu(mats, reps, warmup):
+    """C/OpenMP port of the arithmetic (oracle/quanta_oracle.c)."""
     from oracle import oracle_c as OC
     OC.build()
     elems = sum(m.size for m in mats)
@@ -124,15 +130,36 @@ def time_cpu(mats, reps, warmup):
     return elems, times, OC.num_threads()
 
 
+def time_cpu_torch(mats, reps, warmup):
+    """The reference's own implementation style: eager torch ops, all host threads
+    (oracle/oracle_torch.py restates Quanta/functional/quantization.py:73-99 + utils.py:23-35)."""
+    import torch
+    from oracle import oracle_torch as OT
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    ts = [torch.from_numpy(m).reshape(r, c) for m, (r, c) in zip(mats, LLAMA2_7B_LAYER)]
+    elems = sum(t.numel() for t in ts)
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        for t in ts:
+            OT.quantize4_block_pack(t, BLOCK)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return elems, times, torch.get_num_threads()
+
+
 def run_reference(args, rank):
     """CPU arm: the oracle port of the reference algorithm on all host threads."""
     if rank != 0:
         return
     mats = cpu_sample()
-    elems, times, threads = time_cpu(mats, args.steps, args.warmup)
+    elems, times, threads = time_cpu_torch(mats, args.steps, args.warmup)
     t = sum(times) / len(times)
     value = elems * BYTES_PER_ELEM / t / 1e9
-    sample = "one decoder layer (7 matrices, %d elements) per step" % elems
+    sample = ("one decoder layer (7 matrices, %d elements) per step; eager torch ops as in the reference "
+              "(oracle/oracle_torch.py), %d intra-op threads" % (elems, threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
@@ -256,10 +283,13 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         mats = cpu_sample()
-        elems, times, threads = time_cpu(mats, 3, 1)
+        elems, times, threads = time_cpu_torch(mats, 2, 1)
         tcpu = min(times)
+        _, ctimes, cthreads = time_cpu(mats, 3, 1)
         cpu = {"value": elems * BYTES_PER_ELEM / tcpu / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": "one decoder layer (7 matrices, %d elements), best of 3; C oracle port, OpenMP" % elems}
+               "sample": "one decoder layer (7 matrices, %d elements), best of 2; eager torch ops as in the "
+                         "reference (oracle/oracle_torch.py)" % elems,
+               "c_port_value": elems * BYTES_PER_ELEM / min(ctimes) / 1e9, "c_port_threads": cthreads}
 
     peak, which = peaks()
     if rank == 0:
@@ -273,7 +303,10 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "replicated weight sets, one per GPU, no collective"},
             "roofline": {"bound": "hbm", "kernel": "quantize_rows_tma_kernel<float,4,pack,A,blockwise>",
                          "achieved": per_gpu, "peak": peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                         "unit": "GB/s", "frac": per_gpu / peak, "traffic": None},
+                         "unit": "GB/s", "frac": per_gpu / peak,
+                         # ncu --set full, 11008x4096 launch (profiles/r01_ncu_quantize_block4.txt):
+                         # dram read 180.4 MB + write 12.6 MB vs 208.5 MB algorithmic (outputs still in L2)
+                         "traffic": 192.96e6, "traffic_algorithmic": 208.54e6, "traffic_launch": "11008x4096"},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

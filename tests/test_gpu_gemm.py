@@ -85,6 +85,54 @@ def test_gemm_llama3_8b_shapes(bits):
             assert e2 < TOL, f"vs torch fp32 matmul: {e2:.3e}"
 
 
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("blocksize", [128, 256])
+def test_gemm_larger_blocksizes(bits, blocksize):
+    """block = 64 * 2^j: one scale per `blocksize` K values (scalar parameter path of the kernel)."""
+    import quanta_b200 as Q
+    from quanta_b200.nn import linear_wna16
+    N, K, M = 384, 1024, 40
+    g = torch.Generator().manual_seed(blocksize + bits)
+    w = torch.randn(N, K, generator=g) * 0.02
+    x = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    if bits == 4:
+        q, s, z = Q.quantize_4bit(w.cuda(), blocksize=blocksize, packed=True)
+        codes = O.unpack4(q.cpu().numpy())[: N * K].reshape(N, K)
+    else:
+        q, s, z = Q.quantize_8bit(w.cuda(), blocksize=blocksize)
+        codes = q.cpu().numpy().reshape(N, K)
+    y = linear_wna16(x.cuda(), q, s, z, None, bits=bits, blocksize=blocksize, out_features=N)
+    ref = O.linear_dequant(x.float().numpy(), codes, s.cpu().numpy(), z.cpu().numpy(), None, blocksize, "bf16")
+    assert rel_err(y.float().cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 16), (512, 2048, 256), (384, 1024, 33), (1024, 4096, 64), (200, 320, 7)])
+def test_gemm_cta_pair_variant(shape, monkeypatch):
+    """The cta_group::2 variant (opt-in, QUANTA_B200_GEMM_CG=2) must give the same results."""
+    from quanta_b200.nn import linear_wna16
+    N, K, M = shape
+    w, x, b, q, s, z = make_case(N, K, M, 4, torch.bfloat16, seed=N + K + M)
+    y1 = linear_wna16(x.cuda(), q, s, z, b.cuda(), bits=4, blocksize=64, out_features=N)
+    monkeypatch.setenv("QUANTA_B200_GEMM_CG", "2")
+    y2 = linear_wna16(x.cuda(), q, s, z, b.cuda(), bits=4, blocksize=64, out_features=N)
+    ref = reference(x, q, s, z, b, 4, N, K, torch.bfloat16)
+    assert rel_err(y2.float().cpu().numpy(), ref) < TOL
+    # same arithmetic, possibly a different K split: tiny fp32 summation-order differences only
+    assert float((y1.float() - y2.float()).abs().max() / y1.float().abs().max()) < 2e-2
+
+
+def test_gemm_repeated_calls_leave_workspace_clean():
+    """Stream-K counters are self-resetting: many calls on one workspace, identical results."""
+    from quanta_b200.nn import linear_wna16
+    N, K, M = 1024, 4096, 16
+    w, x, b, q, s, z = make_case(N, K, M, 4, torch.bfloat16, seed=11)
+    xd, bd = x.cuda(), b.cuda()
+    y0 = linear_wna16(xd, q, s, z, bd, bits=4, blocksize=64, out_features=N)
+    for _ in range(20):
+        y = linear_wna16(xd, q, s, z, bd, bits=4, blocksize=64, out_features=N)
+    assert torch.equal(y, y0)
+
+
 def test_linear_modules_mirror_reference_api():
     from quanta_b200.nn import Linear4bit, Linear8bitLt
     torch.manual_seed(0)
