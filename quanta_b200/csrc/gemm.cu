@@ -407,7 +407,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     } else if (warp == 1) {
         // ===== activation tiles: xkb 64-K blocks per slot =====
         if (lane == 0) {
-            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], p.xkb == 4 ? p.nmma : 1); }
+            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
             fence_barrier_init();
             prefetch_tensormap(&tmap_x);
         }
@@ -441,7 +441,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             tmem_alloc_cg<CG>(smem_u32(&tmem_base_slot), kTmemCols);
         } else if (warp == 3 && lane == 0) {
             // a_full / d_empty live in the leader and collect both CTAs' arrivals
-            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], CG * kDqGroupWarps); mbar_init(&a_empty[s], p.nmma); }
+            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], CG * kDqGroupWarps); mbar_init(&a_empty[s], 1); }
             for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], p.nmma); mbar_init(&d_empty[s], CG * kEpiWarps); }
             fence_barrier_init();
         }
@@ -455,10 +455,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
     if (leader && (warp == 2 || (warp == 3 && p.nmma == 2))) {
         // ===== MMA issuers: the whole warp walks the schedule, one elected lane issues =====
-        // A tcgen05.mma costs its issuing warp ~70 cycles of dispatch whatever its size while the
-        // tensor pipe itself needs only N/2 cycles, so for small batches two warps issue: warp 2 the
-        // first two 64-K blocks of every stage, warp 3 the last two, each into its own half of the
-        // rotating accumulators (the epilogue adds all of them up).
+        // A tcgen05.mma costs ~70 cycles of dispatch whatever its size (the tensor pipe itself needs only
+        // N/2 cycles), so a stage is >= 1120 cycles of issue plus ~600 cycles of barrier waits and
+        // commits.  With two issuers (small batches) warp 2 takes the even stages and warp 3 the odd
+        // ones — one dequant group each — so one warp's waits hide behind the other's issue; each
+        // warp rotates over its own half of the accumulators (the epilogue adds all of them up).
         const int mw = warp - 2;
         const uint32_t idesc = (1u << 4) | (AT::kFmt << 7) | (AT::kFmt << 10) |
                                ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)((kTileN * CG) >> 4) << 24);
@@ -475,15 +476,15 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             for (int s = s0; s < s1; ++s, ++sc) {
                 const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
                 const int g = sc & 1;                        // dequant group = A buffer
-                mbar_wait_x<CG>(&a_full[g], (uint32_t)(sc >> 1) & 1u);       // the stage's 4 A tiles are in TMEM
+                if (p.nmma == 1 || g == mw) mbar_wait_x<CG>(&a_full[g], (uint32_t)(sc >> 1) & 1u);   // the stage's 4 A tiles are in TMEM
                 const uint32_t ta = tmem + (uint32_t)(g * kKbPerStage * kACols);
                 TRACE2(2, lane == 0);
 #pragma unroll
                 for (int j = 0; j < kKbPerStage; ++j) {
                     const int jj = j & (p.xkb - 1);
-                    const bool mine = p.nmma == 1 || (j >> 1) == mw;
+                    const bool mine = p.nmma == 1 || (sc & 1) == mw;
                     if (mine) {
-                        if (jj == 0 || (p.nmma == 2 && (j & 1) == 0)) mbar_wait_x<CG>(&x_full[sx], px);    // activation slot landed
+                        if (jj == 0) mbar_wait_x<CG>(&x_full[sx], px);       // activation slot landed
                         tc_fence_after();
                         const bool live = j < nkb && !(p.dbg & 1);
                         uint32_t acc_idx[4], acc_flag[4];    // computed by every lane: stays warp-uniform
@@ -501,11 +502,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                                     umma_f16_ts_cg<CG>(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
                                                 db + 2 * k, idesc, acc_flag[k]);
                             }
-                            // both arrive when the MMAs above have read their operands; with two issuers a
-                            // slot shared by both (xkb = 4) and the A buffer need both warps' commits
-                            const bool last_of_slot = jj == p.xkb - 1 || (p.nmma == 2 && p.xkb == 4 && j == 1);
-                            if (last_of_slot) umma_commit_cg<CG>(&x_empty[sx]);
-                            if (j == kKbPerStage - 1 || (p.nmma == 2 && j == 1)) umma_commit_cg<CG>(&a_empty[g]);
+                            // both arrive when the MMAs above have read their operands
+                            if (jj == p.xkb - 1) umma_commit_cg<CG>(&x_empty[sx]);
+                            if (j == kKbPerStage - 1) umma_commit_cg<CG>(&a_empty[g]);
                         }
                         __syncwarp();
                     }
@@ -523,7 +522,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int row = 32 * quarter + lane;
         const int etid = tid - 32 * kFirstEpiWarp;
         if (etid == 0 && p.y_tma) prefetch_tensormap(&tmap_y);
-        int seg = 0;
+        int seg = 0, esc = 0;                 // esc: CTA-wide stage counter at the start of the segment
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
             const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);
@@ -556,7 +555,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const int last_nkb = (s1 == p.S) ? p.total_kb - (p.S - 1) * kKbPerStage : kKbPerStage;
             int kb_w[2];
             if (p.nmma == 1) { kb_w[0] = (s1 - s0 - 1) * kKbPerStage + last_nkb; kb_w[1] = 0; }
-            else { kb_w[0] = (s1 - s0 - 1) * 2 + min(last_nkb, 2); kb_w[1] = (s1 - s0 - 1) * 2 + max(last_nkb - 2, 0); }
+            else {
+                // warp w issued the stages whose CTA-wide stage counter has parity w
+                kb_w[0] = kb_w[1] = 0;
+                for (int s = s0; s < s1; ++s) kb_w[(esc + (s - s0)) & 1] += (s == p.S - 1) ? last_nkb : kKbPerStage;
+            }
             for (int c0 = 0; c0 < p.mb; c0 += 16) {
                 uint32_t r[16];
 #pragma unroll
@@ -685,6 +688,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // fix_flag is reused
             }
+            esc += s1 - s0;
             ++seg;
         }
     } else if (warp >= kFirstDqWarp) {
@@ -937,10 +941,23 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
 
+// CUDA-core path for decode-sized batches (gemv.cu)
+bool gemv_eligible(int bits, int64_t M, int64_t K, int64_t block);
+template <typename ACT, int BITS>
+int gemv_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, ACT* y, int64_t M,
+                int64_t N, int64_t K, cudaStream_t st);
+
 template <typename ACT, int BITS>
 static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
                        const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
                        cudaStream_t st) {
+    {
+        // M <= 4 on the CUDA cores (gemv.cu): parity-tested, but not faster than the tensor path in round 1
+        // (both end up near 21 us on the Llama shapes), so it is opt-in: QUANTA_B200_GEMV=1
+        const char* e = getenv("QUANTA_B200_GEMV");
+        if (e && e[0] == '1' && gemv_eligible(BITS, M, K, block) && (reinterpret_cast<uintptr_t>(wq) & 15) == 0)
+            return gemv_launch<ACT, BITS>(x, wq, scale, zp, bias, y, M, N, K, st);
+    }
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     const int n_tiles = (int)((N + kTileN - 1) / kTileN);
@@ -961,6 +978,8 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     // accumulators: nbuf x nacc x mb <= 256 TMEM columns
     p.nacc = mb <= 16 ? 8 : (mb <= 64 ? 4 : (mb <= 128 ? 2 : 1));
     p.nbuf = (2 * p.nacc * mb <= kTmemCols - kDBase) ? 2 : 1;
+    // a second MMA-issuing warp (even / odd stages) is implemented but measured no faster: the body is
+    // bound by the dequant groups, not by the issuer (QUANTA_B200_GEMM_NMMA=2 enables it)
     p.nmma = 1;
     if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 2 && p.nacc >= 2) p.nmma = 2; }
     p.dbg = 0;
