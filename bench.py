@@ -198,7 +198,10 @@ def run_ours(args, rank, world, local_rank):
         off += n
 
     def step():
-        return [Q.quantize_4bit(v, blocksize=BLOCK, packed=True) for v in views]
+        # the batched public entry point: the 224 matrices of a step go out in 14 launches
+        if args.per_tensor:
+            return [Q.quantize_4bit(v, blocksize=BLOCK, packed=True) for v in views]
+        return Q.quantize_4bit_many(views, blocksize=BLOCK, packed=True)
 
     def barrier():
         if world > 1:
@@ -234,7 +237,7 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t.item())
     value = world * total * BYTES_PER_ELEM / (ms * 1e-3) / 1e9
     per_gpu = total * BYTES_PER_ELEM / (ms * 1e-3) / 1e9
-    launches = args.steps * len(views)
+    launches = args.steps * (len(views) if args.per_tensor else -(-len(views) // 16))
     del outs, graph
     torch.cuda.empty_cache()
 
@@ -299,9 +302,11 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD, "elements_per_gpu": total, "matrices": len(views), "blocksize": BLOCK,
                        "bytes_per_element": BYTES_PER_ELEM, "l2": "inputs (25.9 GB) larger than L2",
-                       "launch": "224 per-matrix launches replayed as one CUDA graph",
+                       "launch": ("224 per-matrix launches" if args.per_tensor else
+                                  "quantize_4bit_many: 14 multi-tensor launches (16 matrices each)") + " replayed as one CUDA graph",
                        "parallelism": "replicated weight sets, one per GPU, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "quantize_rows_tma_kernel<float,4,pack,A,blockwise>",
+            "roofline": {"bound": "hbm", "kernel": "quantize_rows_tma_kernel<float,4,pack,A,blockwise>" if args.per_tensor
+                         else "quantize_rows_tma_multi_kernel<float,4,pack>",
                          "achieved": per_gpu, "peak": peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                          "unit": "GB/s", "frac": per_gpu / peak,
                          # ncu --set full, 11008x4096 launch (profiles/r01_ncu_quantize_block4.txt):
@@ -325,6 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--per-tensor", action="store_true", help="one quantize_4bit call (launch) per matrix instead of the batched entry")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

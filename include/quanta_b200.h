@@ -90,6 +90,18 @@ QUANTA_API int quanta_quantize_affine(const void* x, int x_dtype, int64_t rows, 
                            uint8_t* q_out, float* scale_out, float* zp_out,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same blockwise quantization (mode BLOCK) over `count` independent
+ * tensors in as few launches as possible — the fused form of the per-parameter
+ * loop of ModelQuantize.quantize (Quanta/functional/model.py:254-289, :60-71),
+ * which calls quantize_*bit once per parameter.  xs / q_outs / scale_outs /
+ * zp_outs are HOST arrays of device pointers, numels[i] the element count of
+ * tensor i (a multiple of `block`); results are identical to `count` calls of
+ * quanta_quantize_affine(..., QUANTA_MODE_BLOCK, ...).                        */
+QUANTA_API int quanta_quantize_block_batch(const void* const* xs, const int64_t* numels, int count, int x_dtype,
+                                int64_t block, int bits, int pack4,
+                                uint8_t* const* q_outs, float* const* scale_outs, float* const* zp_outs,
+                                void* stream);
+
 /* Replaces dequantize_8bit / dequantize_4bit, quant_type="linear"
  * (functional/quantization.py:33-38, :53-58): out = q.float() * scale + zp,
  * multiply and add rounded separately.  packed4 != 0: q holds nibble-packed

@@ -25,6 +25,7 @@ SIGNATURES = {
     "quanta_error_string": (C.c_char_p, [_int]),
     "quanta_workspace_bytes": (_sz, [_int, _i64, _i64]),
     "quanta_quantize_affine": (_int, [_vp, _int, _i64, _i64, _int, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "quanta_quantize_block_batch": (_int, [_vp, _vp, _int, _int, _i64, _int, _int, _vp, _vp, _vp, _vp]),
     "quanta_dequantize_affine": (_int, [_vp, _int, _i64, _i64, _int, _i64, _vp, _vp, _vp, _int, _vp]),
     "quanta_pack4": (_int, [_vp, _i64, _vp, _vp]),
     "quanta_unpack4": (_int, [_vp, _i64, _vp, _vp]),

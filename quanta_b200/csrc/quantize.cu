@@ -561,6 +561,162 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
 }
 
 // --------------------------------------------------------------------------
+// 2b. the same stream over SEVERAL tensors in one launch (blockwise, convention A)
+// --------------------------------------------------------------------------
+// Quantizing a model is hundreds of independent matrices; one launch per matrix pays a
+// prologue (barrier setup, tensor-map fetch, first-tile latency) and a tail each time.  Here up
+// to kMultiMax tensors share one grid: the tile index space is the concatenation of the tensors'
+// tiles, the descriptors ride in the kernel parameters (tensor maps included), and cluster
+// launch control balances the lot.
+constexpr int kMultiMax = 16;
+struct MultiArgs {
+    CUtensorMap maps[kMultiMax];
+    int64_t n_rows[kMultiMax];
+    uint8_t* q[kMultiMax];
+    float* scale[kMultiMax];
+    float* zp[kMultiMax];
+    int tile_base[kMultiMax + 1];     // first global tile of tensor i; [count] = total
+    int count;
+};
+
+template <typename T, int BITS, bool PACK>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+quantize_rows_tma_multi_kernel(const __grid_constant__ MultiArgs a, int log2_lanes_per_block) {
+    using RL = RowLayout<T>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], clc_bar;
+    __shared__ __align__(16) uint4 clc_resp;
+    __shared__ int tile_of_stage[kStages], tens_of_stage[kStages];
+
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = a.tile_base[a.count];
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
+        mbar_init(&clc_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        if (lane == 0) {
+            const uint64_t policy = policy_evict_first();
+            int cta = blockIdx.x;
+            uint32_t clc_phase = 0;
+            for (int i = 0;; ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const bool live = cta >= 0 && cta < n_tiles;
+                if (!live) { tile_of_stage[s] = -1; mbar_arrive(&full_bar[s]); break; }
+                int ti = 0;
+                while (ti + 1 < a.count && cta >= a.tile_base[ti + 1]) ++ti;
+                const int t = cta - a.tile_base[ti];
+                tile_of_stage[s] = t;
+                tens_of_stage[s] = ti;
+                mbar_arrive_expect_tx(&full_bar[s], RL::kTileBytes);
+                tma_load_2d_addr(smem + s * RL::kTileBytes, &a.maps[ti], smem_u32(&full_bar[s]), 0, t * kTileRows, policy);
+                mbar_arrive_expect_tx(&clc_bar, 16);
+                clc_try_cancel(smem_u32(&clc_resp), smem_u32(&clc_bar));
+                mbar_wait(&clc_bar, clc_phase);
+                clc_phase ^= 1;
+                cta = clc_read(smem_u32(&clc_resp));
+            }
+        }
+        return;
+    }
+
+    const int lpb_mask = (1 << log2_lanes_per_block) - 1;
+    const uint32_t row_off = tid * RL::kRowBytes;
+    for (int i = 0;; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        const int t = *reinterpret_cast<volatile int*>(&tile_of_stage[s]);
+        if (t < 0) break;
+        const int ti = *reinterpret_cast<volatile int*>(&tens_of_stage[s]);
+
+        float v[kRowElems];
+        const uint32_t row = smem + s * RL::kTileBytes + row_off;
+#pragma unroll
+        for (int j = 0; j < RL::kChunks; ++j) {
+            uint4 c = lds128(row + (RL::swz(tid, j) << 4));
+            if (sizeof(T) == 4) {
+                v[4 * j + 0] = __uint_as_float(c.x); v[4 * j + 1] = __uint_as_float(c.y);
+                v[4 * j + 2] = __uint_as_float(c.z); v[4 * j + 3] = __uint_as_float(c.w);
+            } else {
+                const T* e = reinterpret_cast<const T*>(&c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * j + k] = to_f32(e[k]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        const int64_t grow = (int64_t)t * kTileRows + tid;
+        const bool row_ok = grow < a.n_rows[ti];
+        uint32_t u[kRowElems];
+        float m0[4], m1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { m0[k] = v[k]; m1[k] = v[k]; }
+#pragma unroll
+        for (int k = 4; k < kRowElems; ++k) { m0[k & 3] = min_nan(m0[k & 3], v[k]); m1[k & 3] = max_nan(m1[k & 3], v[k]); }
+        float mn = min_nan(min_nan(m0[0], m0[1]), min_nan(m0[2], m0[3]));
+        float mx = max_nan(max_nan(m1[0], m1[1]), max_nan(m1[2], m1[3]));
+        for (int o = 1; o <= lpb_mask; o <<= 1) {
+            mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        const float mx2 = (mx == mn) ? __fadd_rn(mn, 1e-6f) : mx;
+        const float range = __fsub_rn(mx2, mn);
+        const bool fast = range >= 8.881784197001252e-16f && range <= 1125899906842624.0f;
+        float scale;
+        if (__all_sync(0xffffffffu, fast)) {
+            scale = div_by_levels<BITS>(range);
+            const float rcp = __frcp_rn(scale);
+            const float nscale = -scale;
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) {
+                const float d = __fsub_rn(v[k], mn);
+                const float q0 = __fmul_rn(d, rcp);
+                const float r = __fmaf_rn(nscale, q0, d);
+                u[k] = __float_as_uint(__fadd_rn(__fmaf_rn(rcp, r, q0), kMagic));
+            }
+        } else {
+            float vs[kRowElems];
+            uint32_t us[kRowElems];
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) vs[k] = v[k];
+            scale = slow_row_codes<BITS>(vs, mn, mx, us);
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) u[k] = us[k];
+        }
+        if (row_ok && (lane & lpb_mask) == 0) {
+            const int64_t b = grow >> log2_lanes_per_block;
+            a.scale[ti][b] = scale;
+            a.zp[ti][b] = mn;
+        }
+        if (row_ok) {
+            if (BITS == 4 && PACK) {
+                uint4 o;
+                o.x = pack_nibbles8<kConvA>(u + 0);  o.y = pack_nibbles8<kConvA>(u + 8);
+                o.z = pack_nibbles8<kConvA>(u + 16); o.w = pack_nibbles8<kConvA>(u + 24);
+                __stcs(reinterpret_cast<uint4*>(a.q[ti] + grow * 16), o);
+            } else {
+                uint32_t w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = pack_bytes4<kConvA, BITS>(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+                uint4* dst = reinterpret_cast<uint4*>(a.q[ti] + grow * 32);
+                __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+                __stcs(dst + 1, make_uint4(w[4], w[5], w[6], w[7]));
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
 // 3. dim-0 quantize: thread owns 4 columns, walks down the rows
 // --------------------------------------------------------------------------
 template <typename T, int BITS, bool PACK, int CONV>
@@ -875,6 +1031,61 @@ static int backend_quantize_t(const T* x, int64_t rows, int64_t cols, int per_ch
                      : quantize_reduced<T, 4, false, kConvBAsym>(x, rows, cols, mode, q, scale, zp, ws, st);
 }
 
+// Blockwise batch: tensors that qualify for the TMA stream go through the multi-tensor kernel in
+// groups of kMultiMax; anything else falls back to a per-tensor launch.
+template <typename T, int BITS, bool PACK>
+static int quantize_block_batch_t(const void* const* xs, const int64_t* numels, int count, int64_t block,
+                                  uint8_t* const* qs, float* const* scales, float* const* zps, cudaStream_t st) {
+    using RL = RowLayout<T>;
+    const bool shape_ok = block % kRowElems == 0 && is_pow2(block / kRowElems) && block <= 1024;
+    auto kern = quantize_rows_tma_multi_kernel<T, BITS, PACK>;
+    const int smem = kStages * RL::kTileBytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    MultiArgs args;
+    args.count = 0;
+    args.tile_base[0] = 0;
+    auto flush = [&]() -> int {
+        if (args.count == 0) return QUANTA_OK;
+        kern<<<(unsigned)args.tile_base[args.count], kTmaThreads, smem, st>>>(args, log2_of(block / kRowElems));
+        args.count = 0;
+        args.tile_base[0] = 0;
+        return cuda_status(cudaGetLastError());
+    };
+    for (int i = 0; i < count; ++i) {
+        const T* x = static_cast<const T*>(xs[i]);
+        const int64_t n = numels[i];
+        if (n <= 0 || n % block != 0) return QUANTA_EINVAL;
+        const int64_t n_rows = n / kRowElems;
+        const int64_t tiles = (n_rows + kTileRows - 1) / kTileRows;
+        if (!shape_ok || !aligned16(x) || !aligned16(qs[i]) || tiles > (int64_t)1 << 24) {
+            int rc = flush();
+            if (rc) return rc;
+            rc = quantize_affine_t<T, BITS, PACK>(x, 1, n, QUANTA_MODE_BLOCK, block, qs[i], scales[i], zps[i], nullptr, st);
+            if (rc) return rc;
+            continue;
+        }
+        if (args.count == kMultiMax || (int64_t)args.tile_base[args.count] + tiles > (int64_t)1 << 30) {
+            int rc = flush();
+            if (rc) return rc;
+        }
+        const int k = args.count;
+        int rc = make_tensor_map_2d(&args.maps[k], TmaType<T>::v, sizeof(T), x, kRowElems, (uint64_t)n_rows, RL::kRowBytes,
+                                    kRowElems, kTileRows,
+                                    sizeof(T) == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        args.n_rows[k] = n_rows;
+        args.q[k] = qs[i]; args.scale[k] = scales[i]; args.zp[k] = zps[i];
+        args.tile_base[k + 1] = args.tile_base[k] + (int)tiles;
+        args.count = k + 1;
+    }
+    return flush();
+}
+
 size_t quantize_workspace_bytes(int64_t cols) {
     size_t tensor_part = (size_t)(kWsHeaderFloats + 64 + 2 * kMaxPartialCtas) * 4;
     size_t dim0_part = (size_t)(kWsHeaderFloats + (int64_t)(2 * kMaxDim0Chunks + 1) * (cols < 1 ? 1 : cols)) * 4;
@@ -931,5 +1142,26 @@ extern "C" int quanta_backend_quantize(const void* x, int x_dtype, int64_t rows,
             return backend_quantize_t(static_cast<const __nv_bfloat16*>(x), rows, cols, per_channel, symmetric, bits,
                                       q_out, scale_out, zp_out, ws, st);
     }
+    return QUANTA_EINVAL;
+}
+
+extern "C" int quanta_quantize_block_batch(const void* const* xs, const int64_t* numels, int count, int x_dtype,
+                                           int64_t block, int bits, int pack4, uint8_t* const* q_outs,
+                                           float* const* scale_outs, float* const* zp_outs, void* stream) {
+    if (!xs || !numels || !q_outs || !scale_outs || !zp_outs || count < 0) return QUANTA_EINVAL;
+    if ((bits != 8 && bits != 4) || (pack4 && bits != 4) || block <= 0) return QUANTA_EINVAL;
+    for (int i = 0; i < count; ++i)
+        if (!xs[i] || !q_outs[i] || !scale_outs[i] || !zp_outs[i]) return QUANTA_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define QUANTA_BATCH(T)                                                                                              \
+    (bits == 8 ? quantize_block_batch_t<T, 8, false>(xs, numels, count, block, q_outs, scale_outs, zp_outs, st)      \
+               : (pack4 ? quantize_block_batch_t<T, 4, true>(xs, numels, count, block, q_outs, scale_outs, zp_outs, st) \
+                        : quantize_block_batch_t<T, 4, false>(xs, numels, count, block, q_outs, scale_outs, zp_outs, st)))
+    switch (x_dtype) {
+        case QUANTA_F32: return QUANTA_BATCH(float);
+        case QUANTA_F16: return QUANTA_BATCH(__half);
+        case QUANTA_BF16: return QUANTA_BATCH(__nv_bfloat16);
+    }
+#undef QUANTA_BATCH
     return QUANTA_EINVAL;
 }

@@ -95,6 +95,54 @@ def quantize_8bit(tensor, quant_type="linear", per_channel=False, blocksize=None
     raise ValueError(f"Unknown quantization type: {quant_type}")
 
 
+def _quantize_many(tensors, bits, blocksize, packed):
+    import ctypes as C
+    tensors = list(tensors)
+    if not tensors:
+        return []
+    B = int(blocksize)
+    dev = tensors[0].device
+    xs, outs = [], []
+    for t in tensors:
+        _host.require_cuda(t)
+        if t.device != dev or t.dtype != tensors[0].dtype:
+            raise ValueError("all tensors of a batch must share one device and dtype")
+        x = t.detach()
+        if not x.is_contiguous():
+            x = x.contiguous()
+        n = x.numel()
+        if n == 0 or n % B:
+            raise ValueError(f"numel ({n}) must be a positive multiple of blocksize ({blocksize})")
+        xs.append(x)
+    code = _host.dtype_code(xs[0])
+    with torch.cuda.device(dev):
+        for x in xs:
+            n = x.numel()
+            q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
+            outs.append((q, torch.empty(n // B, dtype=torch.float32, device=dev),
+                         torch.empty(n // B, dtype=torch.float32, device=dev)))
+        k = len(xs)
+        arr = C.c_void_p * k
+        st = _lib.lib().quanta_quantize_block_batch(
+            arr(*[x.data_ptr() for x in xs]), (C.c_int64 * k)(*[x.numel() for x in xs]), k, code, B, bits,
+            int(bool(packed)), arr(*[o[0].data_ptr() for o in outs]), arr(*[o[1].data_ptr() for o in outs]),
+            arr(*[o[2].data_ptr() for o in outs]), _host.stream_ptr(dev))
+    _lib.check(st, "quanta_quantize_block_batch")
+    return [(q if packed else q.reshape(t.shape), s, z) for (q, s, z), t in zip(outs, tensors)]
+
+
+def quantize_4bit_many(tensors, blocksize=64, packed=True):
+    """Blockwise 4-bit quantization of many tensors in as few launches as possible — the fused form
+    of the per-parameter loop in ``ModelQuantize.quantize`` (Quanta/functional/model.py:254-289).
+    Returns ``[quantize_4bit(t, blocksize=blocksize, packed=packed) for t in tensors]`` (same bits)."""
+    return _quantize_many(tensors, 4, blocksize, packed)
+
+
+def quantize_8bit_many(tensors, blocksize=64):
+    """Blockwise 8-bit twin of :func:`quantize_4bit_many`."""
+    return _quantize_many(tensors, 8, blocksize, False)
+
+
 def _dequantize_linear(q_tensor, scale, zero_point, blocksize, packed, shape, out_dtype):
     _host.require_cuda(q_tensor, "q_tensor")
     dev = q_tensor.device

@@ -321,3 +321,23 @@ def test_full_size_properties(Q):
     # re-quantizing the dequantized tensor reproduces the codes (grid points are fixed points)
     q3, _, _ = Q.quantize_4bit(d, blocksize=64)
     assert (q3 != q).float().mean().item() < 1e-3
+
+
+def test_batched_blockwise_quantize_equals_per_tensor_calls():
+    """quanta_quantize_block_batch: many tensors per launch, bit-identical to one call per tensor
+    (and therefore to the oracle); > 16 tensors exercises several launches, odd sizes the fallback."""
+    import quanta_b200 as Q
+    g = torch.Generator().manual_seed(21)
+    shapes = [(256, 512), (64, 64), (1000, 64), (4096, 1024), (32, 8192)] * 4 + [(3, 64)]
+    ts = [(torch.randn(*s, generator=g) * 0.02).cuda() for s in shapes]
+    for bits, packed in ((4, True), (4, False), (8, False)):
+        many = Q.quantize_4bit_many(ts, blocksize=64, packed=packed) if bits == 4 else Q.quantize_8bit_many(ts, blocksize=64)
+        assert len(many) == len(ts)
+        for t, (q, s, z) in zip(ts, many):
+            q1, s1, z1 = (Q.quantize_4bit(t, blocksize=64, packed=packed) if bits == 4 else Q.quantize_8bit(t, blocksize=64))
+            assert torch.equal(q, q1) and torch.equal(s.view(torch.int32), s1.view(torch.int32))
+            assert torch.equal(z.view(torch.int32), z1.view(torch.int32))
+    # against the oracle directly for one tensor
+    po, so, zo = O.quantize4_block_pack(ts[3].cpu().numpy(), 64)
+    q, s, z = Q.quantize_4bit_many(ts, blocksize=64, packed=True)[3]
+    assert np.array_equal(q.cpu().numpy(), po) and np.array_equal(s.cpu().numpy().view(np.uint32), so.view(np.uint32))
