@@ -111,6 +111,21 @@ QUANTA_API int quanta_dequantize_affine(const uint8_t* q, int packed4, int64_t r
                              int mode, int64_t block, const float* scale, const float* zp,
                              void* out, int out_dtype, void* stream);
 
+/* ---- NF4 codebook: Quanta/functional/quantization.py:101-118, :59-61 --------
+ * quantize_4bit(tensor, quant_type="nf4"): abs_max = max|x|, normalized =
+ * x / abs_max, code = argmin_l |normalized - level_l| (first index on ties,
+ * NaN -> 0).  block = 0: one abs_max for the whole tensor (the reference);
+ * block = 16 * 2^j <= 512: one abs_max per block of flat elements (the
+ * reference function applied to every block), n % block == 0.  q_out: one
+ * code per byte, or nibble-packed (P1 layout) when pack4 != 0; absmax_out: 1
+ * or n / block floats.  dequantize: out = level[code] * abs_max.
+ * quanta_nf4_levels writes the 16-entry table (host memory).               */
+QUANTA_API int quanta_nf4_levels(float* out16);
+QUANTA_API int quanta_quantize_nf4(const void* x, int x_dtype, int64_t n, int64_t block, int pack4,
+                        uint8_t* q_out, float* absmax_out, void* stream);
+QUANTA_API int quanta_dequantize_nf4(const uint8_t* q, int packed4, int64_t n, int64_t block,
+                          const float* absmax, void* out, int out_dtype, void* stream);
+
 /* ---- 4-bit nibble pack / unpack: Quanta/utils/utils.py:23-48 -------------
  * pack:   packed[i] = q[2i] | (q[2i+1] << 4) in uint8 arithmetic, one zero
  *         pad if n is odd; inputs > 15 are not masked (reference behaviour).

@@ -329,3 +329,40 @@ def int8_outlier_matmul(x, qw, cw, threshold=6.0, bias=None, act_dtype="bf16"):
         if bias is not None:
             y = y + np.asarray(bias, np.float64)
         return y, J
+
+
+# --------------------------------------------------------------------------
+# N1 — NF4 codebook quantization (Quanta/functional/quantization.py:101-118, :59-61)
+# --------------------------------------------------------------------------
+
+NF4_LEVELS = np.array([
+    -1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453,
+    -0.28444138169288635, -0.18477343022823334, -0.09105003625154495, 0.0,
+    0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,
+    0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0], dtype=np.float32)
+
+
+def quantize_nf4(x, block=None):
+    """``quantize_4bit_nf4`` (:101-118): abs_max = max|x| (per tensor, or per block of
+    ``block`` flat elements — the reference function applied to each block), normalized =
+    x / abs_max (true divide), index = argmin_l |normalized - level_l| (first index on ties; a NaN
+    distance — 0/0 for an all-zero tensor — wins, i.e. index 0).  Returns (idx uint8, absmax)."""
+    with np.errstate(all="ignore"):
+        x = _f32(x)
+        flat = x.reshape(-1) if block is None else x.reshape(-1, block)
+        ax = np.abs(flat)
+        am = np.max(ax, axis=-1, keepdims=True).astype(np.float32)
+        am = np.where(np.any(np.isnan(ax), axis=-1, keepdims=True), F32(np.nan), am).astype(np.float32)
+        normalized = (flat / am).astype(np.float32)
+        dist = np.abs((normalized[..., None] - NF4_LEVELS).astype(np.float32))
+        idx = np.argmin(dist, axis=-1).astype(np.uint8)
+        return idx.reshape(x.shape), (am.reshape(()) if block is None else am.reshape(-1))
+
+
+def dequantize_nf4(idx, absmax, block=None):
+    """``dequantize_4bit(..., quant_type="nf4")`` (:59-61): levels[q] * abs_max."""
+    idx = np.asarray(idx)
+    lv = NF4_LEVELS[idx.astype(np.int64)]
+    if block is None:
+        return (lv * F32(absmax)).astype(np.float32)
+    return (lv.reshape(-1, block) * _f32(absmax).reshape(-1, 1)).astype(np.float32).reshape(idx.shape)

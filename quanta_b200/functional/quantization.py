@@ -22,7 +22,8 @@ import torch
 
 from .. import _host, _lib
 
-_NOT_BUILT = ("nf4", "fp4", "nf8", "fp8")
+_NOT_BUILT = ("nf4", "fp4", "nf8", "fp8")      # nf4 is built; the others are 'next' rows (N4)
+_nf4_levels = {}
 
 
 def _quantize_linear(tensor, bits, per_channel, blocksize, packed):
@@ -75,12 +76,75 @@ def _quantize_linear(tensor, bits, per_channel, blocksize, packed):
     return q, scale.reshape(pshape), zp.reshape(pshape)
 
 
+def nf4_levels(device):
+    """The 16 NF4 levels as a float32 tensor on ``device`` (second return value of the reference's
+    ``quantize_4bit(..., quant_type="nf4")``, Quanta/functional/quantization.py:105-110)."""
+    import ctypes as C
+    key = str(device)
+    if key not in _nf4_levels:
+        buf = (C.c_float * 16)()
+        _lib.check(_lib.lib().quanta_nf4_levels(buf), "quanta_nf4_levels")
+        _nf4_levels[key] = torch.tensor(list(buf), dtype=torch.float32, device=device)
+    return _nf4_levels[key]
+
+
+def _quantize_nf4(tensor, blocksize, packed):
+    _host.require_cuda(tensor)
+    x = tensor.detach()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    code = _host.dtype_code(x)
+    n = x.numel()
+    if n == 0:
+        raise RuntimeError("max(): cannot quantize an empty tensor")
+    dev = x.device
+    B = 0 if blocksize is None else int(blocksize)
+    if B and n % B:
+        raise ValueError(f"numel ({n}) must be a multiple of blocksize ({blocksize})")
+    with torch.cuda.device(dev):
+        q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
+        absmax = torch.empty(n // B if B else 1, dtype=torch.float32, device=dev)
+        st = _lib.lib().quanta_quantize_nf4(x.data_ptr(), code, n, B, int(bool(packed)), q.data_ptr(),
+                                            absmax.data_ptr(), _host.stream_ptr(dev))
+    _lib.check(st, "quanta_quantize_nf4")
+    if not packed:
+        q = q.reshape(tensor.shape)
+    return q, nf4_levels(dev), (absmax if B else absmax.reshape(()))
+
+
+def _dequantize_nf4(q_tensor, absmax, blocksize, packed, shape, out_dtype):
+    _host.require_cuda(q_tensor, "q_tensor")
+    dev = q_tensor.device
+    q = q_tensor.detach()
+    if q.dtype != torch.uint8:
+        q = q.to(torch.uint8)
+    if not q.is_contiguous():
+        q = q.contiguous()
+    absmax = torch.as_tensor(absmax, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+    out_shape = (torch.Size(shape) if shape is not None else torch.Size([q.numel() * 2])) if packed else q.shape
+    n = out_shape.numel()
+    out = torch.empty(out_shape, dtype=out_dtype, device=dev)
+    if n == 0:
+        return out
+    B = 0 if blocksize is None else int(blocksize)
+    if (B and absmax.numel() != n // B) or (not B and absmax.numel() != 1):
+        raise ValueError("absmax does not match blocksize")
+    with torch.cuda.device(dev):
+        st = _lib.lib().quanta_dequantize_nf4(q.data_ptr(), int(bool(packed)), n, B, absmax.data_ptr(), out.data_ptr(),
+                                              _host._DTYPE[out_dtype], _host.stream_ptr(dev))
+    _lib.check(st, "quanta_dequantize_nf4")
+    return out
+
+
 def quantize_4bit(tensor, quant_type="linear", per_channel=False, blocksize=None, packed=False):
     """Quantize a floating-point tensor to 4-bit precision (codes 0..15, one per
     uint8 unless ``packed``).  Mirrors Quanta/functional/quantization.py:7-18."""
     if quant_type == "linear":
         return _quantize_linear(tensor, 4, per_channel, blocksize, packed)
-    if quant_type in _NOT_BUILT[:2]:
+    if quant_type == "nf4":
+        # returns (indices, nf4_levels, abs_max) like the reference (:118)
+        return _quantize_nf4(tensor, blocksize, packed)
+    if quant_type in _NOT_BUILT[1:2]:
         raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N1/N4), not built yet")
     raise ValueError(f"Unknown quantization type: {quant_type}")
 
@@ -211,6 +275,9 @@ def dequantize_4bit(q_tensor, scale_or_levels, zero_point_or_bias, quant_type="l
     nibble-packed bytes of ``pack_4bit_tensor`` plus the original ``shape``."""
     if quant_type == "linear":
         return _dequantize_linear(q_tensor, scale_or_levels, zero_point_or_bias, blocksize, packed, shape, out_dtype)
-    if quant_type in _NOT_BUILT[:2]:
+    if quant_type == "nf4":
+        # scale_or_levels is the nf4_levels tensor, zero_point_or_bias the abs_max (:59-61)
+        return _dequantize_nf4(q_tensor, zero_point_or_bias, blocksize, packed, shape, out_dtype)
+    if quant_type in _NOT_BUILT[1:2]:
         raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N1/N4), not built yet")
     raise ValueError(f"Unknown quantization type: {quant_type}")
