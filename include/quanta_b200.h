@@ -170,6 +170,14 @@ QUANTA_API int quanta_gemm_wna16(const void* x, int act_dtype, const uint8_t* wq
                       const void* bias, void* y, int64_t M, int64_t N, int64_t K,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same for NF4 weights — Linear4bit's default quant_type="nf4"
+ * (nn/linear.py:58): wq nibble-packed NF4 codes [N, K/2], absmax float32
+ * [N, K/block] (quanta_quantize_nf4 with block | K, block % 64 == 0);
+ * y = x . (level[code] * absmax)[N,K]^T + bias.                            */
+QUANTA_API int quanta_gemm_nf4a16(const void* x, int act_dtype, const uint8_t* wq, const float* absmax,
+                       int64_t block, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* LLM.int8()-style outlier-split matmul for Linear8bitLt.threshold
  * (nn/linear.py:20,25; unused by the reference — semantics defined by this
  * repository, see oracle/oracle_np.py:int8_outlier_matmul).

@@ -180,6 +180,12 @@ __device__ __forceinline__ void dequant_word8(uint32_t w, float s, float zc, uin
     out[1] = ActTraits<ACT>::pack(f[2], f[3]);
 }
 
+__constant__ float kGemmNf4Levels[16] = {
+    -1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,
+    -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,
+    0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f,
+    0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
+
 struct GemmParams {
     int M, N, K;
     int mb;                 // UMMA N: batch rows per tile (multiple of 16, <= 256)
@@ -198,6 +204,7 @@ struct GemmParams {
     int block_shift;        // log2(block / 64)
     int vec4;               // scale / zero-point rows can be read as float4 per stage
     int y_tma;              // whole tiles leave through a TMA store (needs N % 8 == 0 and an aligned y)
+    int nf4;                // 4-bit codes index the NF4 table, `scale` holds abs_max per block, zero-point unused
     int dbg;                // experiment switches (QUANTA_B200_GEMM_DBG): 1 = no MMA, 2 = no dequant math/store
 };
 
@@ -329,6 +336,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     __shared__ uint32_t tmem_base_slot;
     __shared__ int fix_flag;
     __shared__ __align__(1024) float stage[16][kTileN];        // epilogue transpose buffer (8 KB)
+    __shared__ uint32_t nf4_pairs[256];                        // NF4: byte -> (level[lo nibble], level[hi nibble]) in the act type
 #ifdef QUANTA_GEMM_TRACE
     __shared__ long long trace[8][48];
     const bool tr = (p.dbg & 8) && blockIdx.x == 0;
@@ -358,6 +366,10 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     SegWalk walk;
     walk.init(p, cta);
     int tile, s0, s1;
+    if (BITS == 4 && p.nf4 && tid >= 32 * kFirstDqWarp && tid < 32 * kFirstDqWarp + 256) {
+        const int b = tid - 32 * kFirstDqWarp;      // visible to the dequant warps after the CTA-wide barrier below
+        nf4_pairs[b] = AT::pack(kGemmNf4Levels[b & 15], kGemmNf4Levels[b >> 4]);
+    }
 
     // Each producer initialises its own ring, checks in at the CTA-wide barrier without waiting
     // (barrier.arrive) and starts streaming at once; everybody else sees all barriers after
@@ -766,7 +778,22 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     for (int j = 0; j < kKbPerStage; ++j) {
                         if (j < nkb && !(p.dbg & 2)) {
                             uint32_t out[16];
-                            if (BITS == 4) {
+                            if (BITS == 4 && p.nf4) {
+                                // NF4: one shared-memory lookup per code byte gives the K-adjacent pair
+                                // (level[lo], level[hi]); one packed multiply applies the block's abs_max
+                                const V2 s2 = AT::dup(cs[j]);
+                                const uint4 rv = lds128g(rrow + (((uint32_t)(2 * j + half) ^ sw) << 4));
+                                const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        uint32_t pr = nf4_pairs[(w4[i] >> (8 * e)) & 0xFFu];
+                                        V2 v = __hmul2(*reinterpret_cast<V2*>(&pr), s2);
+                                        out[4 * i + e] = *reinterpret_cast<uint32_t*>(&v);
+                                    }
+                                }
+                            } else if (BITS == 4) {
                                 const V2 s2 = AT::dup(cs[j]);
                                 const V2 z2 = AT::dup(__fmaf_rn(8.0f, cs[j], cz[j]));
                                 const uint4 rv = lds128g(rrow + (((uint32_t)(2 * j + half) ^ sw) << 4));
@@ -950,12 +977,12 @@ int gemv_launch(const ACT* x, const uint8_t* wq, const float* scale, const float
 template <typename ACT, int BITS>
 static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
                        const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                       cudaStream_t st) {
+                       cudaStream_t st, int nf4 = 0) {
     {
         // M <= 4 on the CUDA cores (gemv.cu): parity-tested, but not faster than the tensor path in round 1
         // (both end up near 21 us on the Llama shapes), so it is opt-in: QUANTA_B200_GEMV=1
         const char* e = getenv("QUANTA_B200_GEMV");
-        if (e && e[0] == '1' && gemv_eligible(BITS, M, K, block) && (reinterpret_cast<uintptr_t>(wq) & 15) == 0)
+        if (!nf4 && e && e[0] == '1' && gemv_eligible(BITS, M, K, block) && (reinterpret_cast<uintptr_t>(wq) & 15) == 0)
             return gemv_launch<ACT, BITS>(x, wq, scale, zp, bias, y, M, N, K, st);
     }
     GemmParams p;
@@ -983,6 +1010,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     p.nmma = 1;
     if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 2 && p.nacc >= 2) p.nmma = 2; }
     p.dbg = 0;
+    p.nf4 = nf4;
     if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
     p.scale_stride = (int)(K / block);
     int bs = 0; while ((int64_t)(kBlockK << bs) < block) ++bs;
@@ -1015,6 +1043,26 @@ extern "C" int quanta_gemm_wna16(const void* x, int act_dtype, const uint8_t* wq
         using T = __half;
         return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, (T*)y, M, N, K, workspace, workspace_bytes, st)
                          : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, (T*)y, M, N, K, workspace, workspace_bytes, st);
+    }
+    return QUANTA_EINVAL;
+}
+
+extern "C" int quanta_gemm_nf4a16(const void* x, int act_dtype, const uint8_t* wq, const float* absmax, int64_t block,
+                                  const void* bias, void* y, int64_t M, int64_t N, int64_t K, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    if (!x || !wq || !absmax || !y || M <= 0 || N <= 0 || K <= 0) return QUANTA_EINVAL;
+    if (block <= 0 || block % kBlockK != 0 || K % block != 0) return QUANTA_EINVAL;
+    if ((block / kBlockK) & (block / kBlockK - 1)) return QUANTA_EUNSUPPORTED;
+    if ((K / 2) % 16 != 0 || (K * 2) % 16 != 0) return QUANTA_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return QUANTA_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == QUANTA_BF16) {
+        using T = __nv_bfloat16;
+        return gemm_launch<T, 4>((const T*)x, wq, absmax, absmax, block, (const T*)bias, (T*)y, M, N, K, workspace, workspace_bytes, st, 1);
+    }
+    if (act_dtype == QUANTA_F16) {
+        using T = __half;
+        return gemm_launch<T, 4>((const T*)x, wq, absmax, absmax, block, (const T*)bias, (T*)y, M, N, K, workspace, workspace_bytes, st, 1);
     }
     return QUANTA_EINVAL;
 }

@@ -43,6 +43,40 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
     return y.reshape(*x.shape[:-1], N)
 
 
+def linear_nf4a16(x, wq, absmax, bias=None, blocksize=64, out_features=None, in_features=None):
+    """y = x @ (nf4_level[Wq] * absmax).T + bias on the tcgen05 tensor cores — the forward of
+    ``Linear4bit(quant_type="nf4")`` (the reference's default, Quanta/nn/linear.py:58).
+
+    wq      nibble-packed NF4 codes, uint8 [N*K/2] or [N, K/2] (``quantize_4bit(w, "nf4", blocksize=B, packed=True)``)
+    absmax  float32 [N*K/blocksize], blocksize = 64 * 2^j dividing K"""
+    _host.require_cuda(x, "x")
+    if x.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("x must be float16 or bfloat16")
+    K = x.shape[-1]
+    if in_features is not None and in_features != K:
+        raise ValueError(f"x has {K} features, layer expects {in_features}")
+    N = out_features if out_features is not None else (wq.shape[0] if wq.dim() == 2 else None)
+    if N is None:
+        raise ValueError("out_features is required for flat packed weights")
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    dev = x.device
+    y = torch.empty((M, N), dtype=x.dtype, device=dev)
+    if M == 0:
+        return y.reshape(*x.shape[:-1], N)
+    if bias is not None:
+        bias = bias.to(device=dev, dtype=x.dtype).contiguous()
+    with torch.cuda.device(dev):
+        ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+        st = _lib.lib().quanta_gemm_nf4a16(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), absmax.data_ptr(),
+                                           blocksize, bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                           M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
+    _lib.check(st, "quanta_gemm_nf4a16")
+    return y.reshape(*x.shape[:-1], N)
+
+
 def rowwise_quantize_sym(weight):
     """Static int8 weight codes for the outlier-split matmul: convention-B
     symmetric 8-bit with one multiplier per OUTPUT row, i.e.

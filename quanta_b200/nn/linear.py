@@ -9,9 +9,8 @@ along in_features) and ``forward`` is the fused dequantize-then-matmul kernel:
     y = x @ dequantize_*bit(Wq, scale, zero_point).to(x.dtype).T + bias
 
 Parity: defined by that composition; tolerance 1e-2 relative in
-bf16/fp16.  ``quant_type="nf4"`` (the reference default of Linear4bit) is a
-'next' row (N1) and raises NotImplementedError at quantization time; use
-``quant_type="linear"``.
+bf16/fp16.  ``Linear4bit`` supports ``quant_type="nf4"`` (the reference default: NF4 codebook,
+blockwise abs_max) and ``quant_type="linear"`` (blockwise affine).
 """
 from __future__ import annotations
 
@@ -21,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from ..functional.quantization import quantize_4bit, quantize_8bit, dequantize_4bit, dequantize_8bit
-from .functional import linear_wna16, int8_outlier_matmul, rowwise_quantize_sym
+from .functional import linear_wna16, linear_nf4a16, int8_outlier_matmul, rowwise_quantize_sym
 
 
 class _QuantLinearBase(nn.Module):
@@ -147,7 +146,10 @@ class Linear8bitLt(_QuantLinearBase):
 
 
 class Linear4bit(_QuantLinearBase):
-    """4-bit quantized linear layer (Quanta/nn/linear.py:48-83)."""
+    """4-bit quantized linear layer (Quanta/nn/linear.py:48-83).
+
+    ``quant_type="nf4"`` (the reference default): NF4 codebook with one abs_max per block of
+    ``blocksize`` input features; ``quant_type="linear"``: blockwise affine min-max (convention A)."""
     bits = 4
 
     def __init__(self, in_features, out_features, bias=True, compute_dtype=torch.float16, quant_type="nf4",
@@ -158,9 +160,38 @@ class Linear4bit(_QuantLinearBase):
         self._init_common(in_features, out_features, bias, blocksize)
 
     def _check_quant_type(self):
-        if self.quant_type != "linear":
-            raise NotImplementedError(f"quant_type={self.quant_type!r} is a 'next' row (SURVEY §8(f) N1); "
-                                      "only quant_type='linear' is built")
+        if self.quant_type not in ("linear", "nf4"):
+            raise NotImplementedError(f"quant_type={self.quant_type!r} is a 'next' row (SURVEY §8(f) N4); "
+                                      "'nf4' and 'linear' are built")
+
+    @torch.no_grad()
+    def quantize_(self):
+        if self.quant_type != "nf4":
+            return super().quantize_()
+        w = self.weight.detach()
+        if self.in_features % self.blocksize:
+            raise ValueError(f"in_features ({self.in_features}) must be a multiple of blocksize ({self.blocksize})")
+        # scale holds abs_max per block; there is no zero-point
+        self.qweight, _, self.scale = quantize_4bit(w, quant_type="nf4", blocksize=self.blocksize, packed=True)
+        self.zero_point = None
+        self.weight = nn.Parameter(torch.empty(0, device=w.device), requires_grad=False)
+        return self
+
+    def dequantize_weight(self, dtype=torch.float32):
+        if self.quant_type != "nf4":
+            return super().dequantize_weight(dtype)
+        return dequantize_4bit(self.qweight, None, self.scale, quant_type="nf4", blocksize=self.blocksize, packed=True,
+                               shape=(self.out_features, self.in_features), out_dtype=dtype)
 
     def forward(self, x):
-        return self._forward_quantized(x, self.compute_dtype)
+        if self.quant_type != "nf4":
+            self._check_quant_type()
+            return self._forward_quantized(x, self.compute_dtype)
+        if self.qweight is None:
+            if not self.weight.is_cuda:
+                raise RuntimeError("quanta_b200 layers run on CUDA only: move the module to a GPU first")
+            self.quantize_()
+        xin = x if x.dtype == self.compute_dtype else x.to(self.compute_dtype)
+        y = linear_nf4a16(xin, self.qweight, self.scale, self.bias, blocksize=self.blocksize,
+                          out_features=self.out_features, in_features=self.in_features)
+        return y if y.dtype == x.dtype or not x.is_floating_point() else y.to(x.dtype)

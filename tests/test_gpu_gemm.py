@@ -152,4 +152,40 @@ def test_linear_modules_mirror_reference_api():
         ref_fp = torch.nn.functional.linear(x.float(), w.float(), lin.bias.float())
         assert float((y.float() - ref_fp).abs().max() / ref_fp.abs().max()) < (0.15 if lin.bits == 4 else 0.02)
     with pytest.raises(NotImplementedError):
-        Linear4bit(64, 64).cuda()(torch.randn(1, 64, device="cuda", dtype=torch.float16))   # default quant_type="nf4"
+        Linear4bit(64, 64, quant_type="fp4").cuda()(torch.randn(1, 64, device="cuda", dtype=torch.float16))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(128, 64, 1), (256, 512, 16), (384, 1024, 33), (1024, 4096, 64), (512, 2048, 256),
+                                   (200, 320, 7)])
+def test_nf4_gemm_matches_composition_oracle(dtype, shape):
+    """F.linear(x, dequantize_4bit(idx, levels, absmax, "nf4").to(x.dtype)) in float64 (codes are bit-exact with
+    the reference, tests/test_gpu_nf4.py)."""
+    import quanta_b200 as Q
+    from quanta_b200.nn import linear_nf4a16
+    N, K, M = shape
+    g = torch.Generator().manual_seed(N + K + M)
+    w = torch.randn(N, K, generator=g) * 0.02
+    x = torch.randn(M, K, generator=g).to(dtype)
+    b = (torch.randn(N, generator=g) * 0.1).to(dtype)
+    q, levels, am = Q.quantize_4bit(w.cuda(), quant_type="nf4", blocksize=64, packed=True)
+    y = linear_nf4a16(x.cuda(), q, am, b.cuda(), blocksize=64, out_features=N)
+    idx = O.unpack4(q.cpu().numpy())[: N * K].reshape(N, K)
+    wd = O.dequantize_nf4(idx, am.cpu().numpy(), 64)
+    wd = O._round_to(wd, "bf16" if dtype == torch.bfloat16 else "fp16")
+    ref = x.float().numpy().astype(np.float64) @ wd.astype(np.float64).T + b.float().numpy().astype(np.float64)
+    assert rel_err(y.float().cpu().numpy(), ref) < TOL
+
+
+def test_linear4bit_default_is_nf4():
+    from quanta_b200.nn import Linear4bit
+    torch.manual_seed(1)
+    lin = Linear4bit(512, 256).cuda()                      # reference defaults: compute_dtype=float16, quant_type="nf4"
+    w = lin.weight.detach().clone()
+    x = torch.randn(5, 512, device="cuda", dtype=torch.float16)
+    y = lin(x)
+    assert y.shape == (5, 256) and y.dtype == torch.float16
+    ref = torch.nn.functional.linear(x.float(), lin.dequantize_weight(torch.float16).float(), lin.bias.float())
+    assert float((y.float() - ref).abs().max() / ref.abs().max()) < TOL
+    ref_fp = torch.nn.functional.linear(x.float(), w.float(), lin.bias.float())
+    assert float((y.float() - ref_fp).abs().max() / ref_fp.abs().max()) < 0.15
