@@ -7,13 +7,14 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import quanta_b200 as Q
-from quanta_b200.nn import linear_wna16
+from quanta_b200.nn import linear_wna16, linear_nf4a16
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=24)
 ap.add_argument("--out", default=None)
 ap.add_argument("--ms", default="1,8,16,32,64,128,256")
 ap.add_argument("--dtype", default="bf16")
+ap.add_argument("--formats", default="4,8", help="comma list of 4, 8, nf4")
 args = ap.parse_args()
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 try:
@@ -24,17 +25,26 @@ except Exception:
 dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
 lines = []
 for (N, K) in ((4096, 14336), (14336, 4096)):
-    for bits in (4, 8):
-        wbytes = N * K * bits // 8 + (N * K // 64) * 8
+    for fmt in args.formats.split(","):
+        nf4 = fmt == "nf4"
+        bits = 4 if nf4 else int(fmt)
+        wbytes = N * K * bits // 8 + (N * K // 64) * (4 if nf4 else 8)
         copies = max(4, int(400e6 // wbytes) + 1)
         ws = []
         for i in range(copies):
             w = torch.randn(N, K, device="cuda") * 0.02
-            ws.append(Q.quantize_4bit(w, blocksize=64, packed=True) if bits == 4 else Q.quantize_8bit(w, blocksize=64))
+            if nf4:
+                q_, _, am_ = Q.quantize_4bit(w, quant_type="nf4", blocksize=64, packed=True)
+                ws.append((q_, am_))
+            else:
+                ws.append(Q.quantize_4bit(w, blocksize=64, packed=True) if bits == 4 else Q.quantize_8bit(w, blocksize=64))
             del w
         for M in [int(v) for v in args.ms.split(",")]:
             x = torch.randn(M, K, device="cuda").to(dt)
-            fn = lambda i: linear_wna16(x, *ws[i % copies], None, bits=bits, blocksize=64, out_features=N)
+            if nf4:
+                fn = lambda i: linear_nf4a16(x, *ws[i % copies], None, blocksize=64, out_features=N)
+            else:
+                fn = lambda i: linear_wna16(x, *ws[i % copies], None, bits=bits, blocksize=64, out_features=N)
             for i in range(3):
                 fn(i)
             torch.cuda.synchronize()
@@ -55,7 +65,7 @@ for (N, K) in ((4096, 14336), (14336, 4096)):
             abytes = wbytes + 2 * M * K + 2 * M * N
             t_hbm, t_tc = abytes / HBM / 1e3, flops / TFS / 1e6          # microseconds
             bound = "hbm" if t_hbm >= t_tc else "tensor"
-            line = {"op": f"W{bits}A16", "N": N, "K": K, "M": M, "dtype": args.dtype, "us": round(us, 2),
+            line = {"op": "NF4A16" if nf4 else f"W{bits}A16", "N": N, "K": K, "M": M, "dtype": args.dtype, "us": round(us, 2),
                     "TFLOPs": round(flops / us / 1e6, 1), "GBps": round(abytes / us / 1e3, 1), "bound": bound,
                     "frac_of_roof": round(max(t_hbm, t_tc) / us, 3), "t_hbm_us": round(t_hbm, 2), "t_tensor_us": round(t_tc, 2)}
             print(json.dumps(line), flush=True)

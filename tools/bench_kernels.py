@@ -124,6 +124,28 @@ n = shape[0] * shape[1]
 timeit("quantize_4bit block64 +pack, bf16 input", shape, n * 2.625, lambda i: randn(shape, i).to(torch.bfloat16),
        lambda x: Q.quantize_4bit(x, blocksize=64, packed=True), 6)
 
+# NF4 (row N1): per tensor (two passes) and blockwise, quantize and dequantize
+timeit("quantize_4bit nf4 per-tensor (N1, two-pass)", shape, n * 5.0, lambda i: randn(shape, i),
+       lambda x: Q.quantize_4bit(x, quant_type="nf4"), 3)
+timeit("quantize_4bit nf4 block64 +pack (N1)", shape, n * (4 + 0.5 + 4 / 64), lambda i: randn(shape, i),
+       lambda x: Q.quantize_4bit(x, quant_type="nf4", blocksize=64, packed=True), 3)
+
+
+def mk_nf4(i):
+    q, lv, am = Q.quantize_4bit(randn(shape, i), quant_type="nf4", blocksize=64, packed=True)
+    return q, lv, am
+
+
+timeit("dequantize_4bit nf4 packed block64 -> fp32 (N1)", shape, n * (0.5 + 4 + 4 / 64), mk_nf4,
+       lambda t: Q.dequantize_4bit(*t, quant_type="nf4", blocksize=64, packed=True, shape=shape), 3)
+
+# batched blockwise quantize (one decoder layer's 7 matrices per call)
+layer = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+nl = sum(a * b for a, b in layer)
+timeit("quantize_4bit_many block64 +pack, one Llama-2-7B layer (7 matrices)", (nl,), nl * 4.625,
+       lambda i: [randn(sh, 10 * i + j) for j, sh in enumerate(layer)],
+       lambda ts: Q.quantize_4bit_many(ts, blocksize=64, packed=True), 2)
+
 if args.out:
     with open(args.out, "w") as f:
         for l in lines:
