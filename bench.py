@@ -309,9 +309,13 @@ def run_ours(args, rank, world, local_rank):
                          else "quantize_rows_tma_multi_kernel<float,4,pack>",
                          "achieved": per_gpu, "peak": peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                          "unit": "GB/s", "frac": per_gpu / peak,
-                         # ncu --set full, 11008x4096 launch (profiles/r01_ncu_quantize_block4.txt):
-                         # dram read 180.4 MB + write 12.6 MB vs 208.5 MB algorithmic (outputs still in L2)
-                         "traffic": 192.96e6, "traffic_algorithmic": 208.54e6, "traffic_launch": "11008x4096"},
+                         # ncu --set full (profiles/r01_ncu_quantize_multi.txt), one multi-tensor launch over a
+                         # decoder layer's 7 matrices: dram read 809.6 MB + write 80.5 MB vs 936.0 MB algorithmic
+                         # (part of the outputs is still in L2 when the kernel ends); per-matrix launch
+                         # 11008x4096: 193.0 MB vs 208.5 MB (profiles/r01_ncu_quantize_block4.txt)
+                         "traffic": 193.0e6 if args.per_tensor else 890.1e6,
+                         "traffic_algorithmic": 208.5e6 if args.per_tensor else 936.0e6,
+                         "traffic_launch": "11008x4096" if args.per_tensor else "one decoder layer (7 matrices) per launch"},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
