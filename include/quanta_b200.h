@@ -170,6 +170,19 @@ QUANTA_API int quanta_gemm_wna16(const void* x, int act_dtype, const uint8_t* wq
                       const void* bias, void* y, int64_t M, int64_t N, int64_t K,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Column-parallel form of quanta_gemm_wna16 (the tensor-parallel
+ * Linear*: rank r holds rows [col0, col0+N) of the weight).  The tile epilogue
+ * writes y[:, col0:col0+N] into EVERY buffer of `ys` (host array of n_out <= 8
+ * device pointers, row pitch `ldy` elements >= col0 + N): the local y and the
+ * peer-mapped y of the other ranks (CUDA IPC / symmetric memory over NVLink),
+ * so the output all-gather happens inside the GEMM.  The caller orders the
+ * ranks afterwards (one cross-rank barrier) before reading y.              */
+QUANTA_API int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uint8_t* wq, int bits,
+                              const float* scale, const float* zp, int64_t block,
+                              const void* bias, void* const* ys, int n_out, int64_t ldy, int64_t col0,
+                              int64_t M, int64_t N, int64_t K,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* The same for NF4 weights — Linear4bit's default quant_type="nf4"
  * (nn/linear.py:58): wq nibble-packed NF4 codes [N, K/2], absmax float32
  * [N, K/block] (quanta_quantize_nf4 with block | K, block % 64 == 0);

@@ -186,6 +186,12 @@ __constant__ float kGemmNf4Levels[16] = {
     0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f,
     0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
 
+constexpr int kMaxOut = 8;
+struct GemmOutputs {
+    CUtensorMap maps[kMaxOut];      // TMA-store maps of the output buffers ([M, col0 + N] windows, pitch ldy)
+    void* y[kMaxOut];
+};
+
 struct GemmParams {
     int M, N, K;
     int mb;                 // UMMA N: batch rows per tile (multiple of 16, <= 256)
@@ -203,7 +209,11 @@ struct GemmParams {
     int scale_stride;       // K / block
     int block_shift;        // log2(block / 64)
     int vec4;               // scale / zero-point rows can be read as float4 per stage
+    int vec_store;          // 8-byte stores of 4 outputs are aligned in every output buffer
     int y_tma;              // whole tiles leave through a TMA store (needs N % 8 == 0 and an aligned y)
+    int n_out;              // output buffers (1, or one per tensor-parallel peer: the tile is written to all of them)
+    int ldy;                // row pitch of y in elements (N, or the full out_features of a column-parallel layer)
+    int col0;               // first output column of this call inside y
     int nf4;                // 4-bit codes index the NF4 table, `scale` holds abs_max per block, zero-point unused
     int dbg;                // experiment switches (QUANTA_B200_GEMM_DBG): 1 = no MMA, 2 = no dequant math/store
 };
@@ -326,8 +336,8 @@ template <typename ACT, int BITS, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_z,
-                  const __grid_constant__ CUtensorMap tmap_y, const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
-                  ACT* __restrict__ y, unsigned int* __restrict__ counters, float* __restrict__ partial,
+                  const __grid_constant__ GemmOutputs outs, const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
+                  unsigned int* __restrict__ counters, float* __restrict__ partial,
                   const __grid_constant__ GemmParams p) {
     using AT = ActTraits<ACT>;
     extern __shared__ uint8_t smem_raw[];
@@ -533,7 +543,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int quarter = warp & 3;
         const int row = 32 * quarter + lane;
         const int etid = tid - 32 * kFirstEpiWarp;
-        if (etid == 0 && p.y_tma) prefetch_tensormap(&tmap_y);
+        if (etid == 0 && p.y_tma) { for (int o = 0; o < p.n_out; ++o) prefetch_tensormap(&outs.maps[o]); }
         int seg = 0, esc = 0;                 // esc: CTA-wide stage counter at the start of the segment
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
@@ -560,7 +570,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             float b4[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? AT::to_float(bias[gn4 + e]) : 0.0f;
-            const bool vec_ok = (p.N & 3) == 0 && gn4 + 3 < p.N && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+            const bool vec_ok = p.vec_store && gn4 + 3 < p.N;
             // accumulators the MMA warps wrote in this segment: each warp issues 4 MMAs per 64-K block of
             // its half of the stage (all of it with one issuer), rotating over its own my_acc accumulators
             const int my_acc = p.nacc / p.nmma;
@@ -599,8 +609,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     fence_proxy_async_smem();
                     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                     if (etid == 0 && c0 < m_valid) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(reinterpret_cast<uint64_t>(&tmap_y)), "r"(smem_u32(sbuf)), "r"(n_tile * kTileN), "r"(m0 + c0) : "memory");
+                        // one store per output buffer: the local y, or every tensor-parallel peer's y over NVLink
+                        for (int o = 0; o < p.n_out; ++o)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&outs.maps[o])), "r"(smem_u32(sbuf)),
+                                           "r"(p.col0 + n_tile * kTileN), "r"(m0 + c0) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     continue;
@@ -619,16 +632,18 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         if (m < m_valid) {
                             const float4 v = *reinterpret_cast<const float4*>(&stage[ml][f4]);
                             if (whole) {
-                                ACT* dst = y + (int64_t)(m0 + m) * p.N + gn4;
                                 const float o[4] = {v.x + b4[0], v.y + b4[1], v.z + b4[2], v.w + b4[3]};
-                                if (vec_ok) {
-                                    uint2 pk;
-                                    pk.x = AT::pack(o[0], o[1]);
-                                    pk.y = AT::pack(o[2], o[3]);
-                                    *reinterpret_cast<uint2*>(dst) = pk;
-                                } else {
+                                for (int ob = 0; ob < p.n_out; ++ob) {
+                                    ACT* dst = static_cast<ACT*>(outs.y[ob]) + (int64_t)(m0 + m) * p.ldy + p.col0 + gn4;
+                                    if (vec_ok) {
+                                        uint2 pk;
+                                        pk.x = AT::pack(o[0], o[1]);
+                                        pk.y = AT::pack(o[2], o[3]);
+                                        *reinterpret_cast<uint2*>(dst) = pk;
+                                    } else {
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                                        for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                                    }
                                 }
                             } else {
                                 *reinterpret_cast<float4*>(mine + m * kTileN + f4) = v;
@@ -683,16 +698,18 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         for (int i = 0; i < 8; ++i) {
                             const int m = mb0 + 4 * i;
                             if (m < m_valid) {
-                                ACT* dst = y + (int64_t)(m0 + m) * p.N + gn4;
                                 const float o[4] = {acc[i].x + b4[0], acc[i].y + b4[1], acc[i].z + b4[2], acc[i].w + b4[3]};
-                                if (vec_ok) {
-                                    uint2 pk;
-                                    pk.x = AT::pack(o[0], o[1]);
-                                    pk.y = AT::pack(o[2], o[3]);
-                                    *reinterpret_cast<uint2*>(dst) = pk;
-                                } else {
+                                for (int ob = 0; ob < p.n_out; ++ob) {
+                                    ACT* dst = static_cast<ACT*>(outs.y[ob]) + (int64_t)(m0 + m) * p.ldy + p.col0 + gn4;
+                                    if (vec_ok) {
+                                        uint2 pk;
+                                        pk.x = AT::pack(o[0], o[1]);
+                                        pk.y = AT::pack(o[2], o[3]);
+                                        *reinterpret_cast<uint2*>(dst) = pk;
+                                    } else {
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                                        for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                                    }
                                 }
                             }
                         }
@@ -889,7 +906,7 @@ size_t gemm_workspace_bytes(int64_t M, int64_t) {
 
 template <typename ACT, int BITS, int CG>
 static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const float* scale, const float* zp,
-                          const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
+                          const ACT* bias, void* const* ys, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
                           cudaStream_t st) {
     const int mb = p.mb;
     const int tiles = p.n_tiles * p.m_tiles;               // scheduling tiles: CG adjacent 128-feature tiles each
@@ -938,13 +955,26 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
                                 (uint64_t)p.scale_stride * 4, kKbPerStage, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
-    CUtensorMap tmap_y = tmap_w;
-    p.y_tma = ((N & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
+    GemmOutputs outs;
+    bool aligned16 = true, aligned8 = true;
+    for (int o = 0; o < kMaxOut; ++o) {
+        outs.maps[o] = tmap_w;                              // placeholder
+        outs.y[o] = o < p.n_out ? ys[o] : nullptr;
+        if (o < p.n_out) {
+            aligned16 = aligned16 && (reinterpret_cast<uintptr_t>(ys[o]) & 15) == 0;
+            aligned8 = aligned8 && (reinterpret_cast<uintptr_t>(ys[o]) & 7) == 0;
+        }
+    }
+    p.vec_store = (aligned8 && (p.ldy & 3) == 0 && (p.col0 & 3) == 0) ? 1 : 0;
+    p.y_tma = (aligned16 && (p.ldy & 7) == 0) ? 1 : 0;
     if (const char* e = getenv("QUANTA_B200_GEMM_YTMA")) { if (atoi(e) == 0) p.y_tma = 0; }
     if (p.y_tma) {
-        rc = make_tensor_map_2d(&tmap_y, ActTraits<ACT>::kTma, 2, y, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, kTileN, 16,
-                                CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc) return rc;
+        // window [M, col0 + N] of each buffer: features past this call's columns are clipped by the map
+        for (int o = 0; o < p.n_out; ++o) {
+            rc = make_tensor_map_2d(&outs.maps[o], ActTraits<ACT>::kTma, 2, ys[o], (uint64_t)(p.col0 + N), (uint64_t)M,
+                                    (uint64_t)p.ldy * 2, kTileN, 16, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
     }
     auto kern = gemm_wna16_kernel<ACT, BITS, CG>;
     const int smem = (int)(p.x_ring_off + (uint32_t)p.x_stages * p.x_slot_bytes + 1024);
@@ -964,7 +994,7 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CG == 2 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_x, tmap_s, tmap_z, tmap_y, scale, zp, bias, y, counters, partial, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_x, tmap_s, tmap_z, outs, scale, zp, bias, counters, partial, p);
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
 
@@ -977,12 +1007,15 @@ int gemv_launch(const ACT* x, const uint8_t* wq, const float* scale, const float
 template <typename ACT, int BITS>
 static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
                        const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                       cudaStream_t st, int nf4 = 0) {
+                       cudaStream_t st, int nf4 = 0, void* const* ys = nullptr, int n_out = 1, int64_t ldy = 0,
+                       int64_t col0 = 0) {
+    void* one[1] = {y};
+    if (!ys) { ys = one; n_out = 1; ldy = N; col0 = 0; }
     {
         // M <= 4 on the CUDA cores (gemv.cu): parity-tested, but not faster than the tensor path in round 1
         // (both end up near 21 us on the Llama shapes), so it is opt-in: QUANTA_B200_GEMV=1
         const char* e = getenv("QUANTA_B200_GEMV");
-        if (!nf4 && e && e[0] == '1' && gemv_eligible(BITS, M, K, block) && (reinterpret_cast<uintptr_t>(wq) & 15) == 0)
+        if (!nf4 && n_out == 1 && ldy == N && e && e[0] == '1' && gemv_eligible(BITS, M, K, block) && (reinterpret_cast<uintptr_t>(wq) & 15) == 0)
             return gemv_launch<ACT, BITS>(x, wq, scale, zp, bias, y, M, N, K, st);
     }
     GemmParams p;
@@ -1011,14 +1044,15 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 2 && p.nacc >= 2) p.nmma = 2; }
     p.dbg = 0;
     p.nf4 = nf4;
+    p.n_out = n_out; p.ldy = (int)ldy; p.col0 = (int)col0;
     if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
     p.scale_stride = (int)(K / block);
     int bs = 0; while ((int64_t)(kBlockK << bs) < block) ++bs;
     p.block_shift = bs;
     p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
               ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
-    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2>(p, x, wq, scale, zp, bias, y, M, N, K, workspace, ws_bytes, st);
-    return gemm_launch_cg<ACT, BITS, 1>(p, x, wq, scale, zp, bias, y, M, N, K, workspace, ws_bytes, st);
+    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+    return gemm_launch_cg<ACT, BITS, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
 }
 
 }  // namespace quanta
@@ -1063,6 +1097,31 @@ extern "C" int quanta_gemm_nf4a16(const void* x, int act_dtype, const uint8_t* w
     if (act_dtype == QUANTA_F16) {
         using T = __half;
         return gemm_launch<T, 4>((const T*)x, wq, absmax, absmax, block, (const T*)bias, (T*)y, M, N, K, workspace, workspace_bytes, st, 1);
+    }
+    return QUANTA_EINVAL;
+}
+
+extern "C" int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uint8_t* wq, int bits, const float* scale,
+                                         const float* zp, int64_t block, const void* bias, void* const* ys, int n_out,
+                                         int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    if (!x || !wq || !scale || !zp || !ys || n_out < 1 || n_out > kMaxOut || M <= 0 || N <= 0 || K <= 0) return QUANTA_EINVAL;
+    if (ldy < col0 + N || col0 < 0) return QUANTA_EINVAL;
+    for (int o = 0; o < n_out; ++o) if (!ys[o]) return QUANTA_EINVAL;
+    if ((bits != 4 && bits != 8) || block <= 0 || block % kBlockK != 0 || K % block != 0) return QUANTA_EINVAL;
+    if ((block / kBlockK) & (block / kBlockK - 1)) return QUANTA_EUNSUPPORTED;
+    if ((K * bits / 8) % 16 != 0 || (K * 2) % 16 != 0) return QUANTA_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return QUANTA_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == QUANTA_BF16) {
+        using T = __nv_bfloat16;
+        return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0)
+                         : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0);
+    }
+    if (act_dtype == QUANTA_F16) {
+        using T = __half;
+        return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0)
+                         : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0);
     }
     return QUANTA_EINVAL;
 }

@@ -43,6 +43,39 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
     return y.reshape(*x.shape[:-1], N)
 
 
+def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=64, out_features=None):
+    """``linear_wna16`` whose epilogue writes this rank's output columns into every buffer
+    of ``outs``: ``y_o[:, col0:col0+N] = x @ dequant(Wq).T + bias`` for each ``y_o``.
+
+    outs   (device pointers, ldy): [M, ldy] buffers of x's dtype with the same row pitch —
+           the local output and the peer-mapped outputs of the other ranks
+    Returns nothing; the caller synchronises the ranks before reading."""
+    import ctypes
+    _host.require_cuda(x, "x")
+    if x.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("x must be float16 or bfloat16")
+    K = x.shape[-1]
+    N = out_features if out_features is not None else wq.shape[0]
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    ptrs, ldy = outs
+    if M == 0 or N == 0:
+        return
+    dev = x.device
+    if bias is not None:
+        bias = bias.to(device=dev, dtype=x.dtype).contiguous()
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    with torch.cuda.device(dev):
+        ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+        st = _lib.lib().quanta_gemm_wna16_scatter(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits,
+                                                  scale.data_ptr(), zp.data_ptr(), blocksize,
+                                                  bias.data_ptr() if bias is not None else None, arr, len(ptrs), ldy,
+                                                  col0, M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
+    _lib.check(st, "quanta_gemm_wna16_scatter")
+
+
 def linear_nf4a16(x, wq, absmax, bias=None, blocksize=64, out_features=None, in_features=None):
     """y = x @ (nf4_level[Wq] * absmax).T + bias on the tcgen05 tensor cores — the forward of
     ``Linear4bit(quant_type="nf4")`` (the reference's default, Quanta/nn/linear.py:58).

@@ -7,8 +7,16 @@ scales are exactly the corresponding slices of the unsharded result.
 
 The tensor-parallel linear is column-parallel: rank r holds the quantized rows
 ``[r0, r1)`` of W, computes ``y_r[M, r1-r0] = x @ dequant(W_r).T + b_r`` with the
-same fused kernel, and ONE all-gather (NCCL over NVLink on the GPU box, gloo
-in the CPU tests) assembles ``y[M, out]`` — the only exchange step on the path.
+same fused kernel, and the ranks' columns are assembled into ``y[M, out]`` —
+the only exchange step on the path — in one of two ways:
+
+* ``fused_gather=False``: ONE all-gather (NCCL over NVLink on the GPU box, gloo
+  in the CPU tests) after the kernel;
+* ``fused_gather=True`` (CUDA, one box): the GEMM's tile epilogue stores each
+  finished tile straight into EVERY rank's ``y`` (peer-mapped symmetric memory,
+  TMA stores over NVLink), so the gather overlaps the math tile by tile and the
+  only thing after the kernel is a cross-rank barrier on the stream.
+
 One process per GPU; ``torch.distributed`` is plumbing only.
 """
 from __future__ import annotations
@@ -67,7 +75,7 @@ class TensorParallelLinear(nn.Module):
     the ranks' output columns.  ``bits`` = 4 (packed) or 8."""
 
     def __init__(self, in_features, out_features, bits=4, bias=True, compute_dtype=torch.bfloat16, blocksize=64,
-                 group=None):
+                 group=None, fused_gather=False, max_rows=256):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.bits, self.blocksize, self.compute_dtype, self.group = bits, blocksize, compute_dtype, group
@@ -79,6 +87,22 @@ class TensorParallelLinear(nn.Module):
         self.register_buffer("zero_point", None)
         self.register_buffer("bias", None)
         self._has_bias = bias
+        self.fused_gather = bool(fused_gather) and self.world_size > 1
+        self.max_rows = max_rows
+        self._sym = None
+
+    def _symmetric_outputs(self, device):
+        """Two [max_rows, out_features] output buffers in symmetric memory, mapped into every
+        rank of the group.  Two, because a peer may already be writing call n+1's tiles while
+        this rank's consumers still read call n's y; the barrier of call n+1 orders call n+2's
+        writes behind them (everything runs on the caller's stream)."""
+        if self._sym is None:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            buf = symm.empty((2, self.max_rows, self.out_features), dtype=self.compute_dtype, device=device)
+            hdl = symm.rendezvous(buf, grp)
+            self._sym = {"buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs], "turn": 0}
+        return self._sym
 
     @torch.no_grad()
     def load_shard(self, weight_rows, bias_rows=None):
@@ -105,6 +129,25 @@ class TensorParallelLinear(nn.Module):
     def forward(self, x):
         xin = x if x.dtype == self.compute_dtype else x.to(self.compute_dtype)
         lead = xin.shape[:-1]
-        y_local = self.local_matmul(xin.reshape(-1, self.in_features))
+        x2 = xin.reshape(-1, self.in_features)
+        if self.fused_gather and x2.shape[0] <= self.max_rows:
+            return self._forward_fused(x2).reshape(*lead, self.out_features)
+        y_local = self.local_matmul(x2)
         y = gather_columns(y_local, self.out_features, self.group, 128)
         return y.reshape(*lead, self.out_features)
+
+    def _forward_fused(self, x2):
+        """GEMM with the gather in its epilogue.  Returns a view of the symmetric output buffer:
+        valid until the call after next on this layer (copy it to keep it longer)."""
+        from .nn.functional import linear_wna16_scatter
+        sym = self._symmetric_outputs(x2.device)
+        turn = sym["turn"]
+        sym["turn"] = turn ^ 1
+        M = x2.shape[0]
+        slot = turn * self.max_rows * self.out_features * x2.element_size()
+        r0, r1 = self.rows
+        linear_wna16_scatter(x2, self.qweight, self.scale, self.zero_point, self.bias,
+                             ([p + slot for p in sym["ptrs"]], self.out_features), r0, bits=self.bits,
+                             blocksize=self.blocksize, out_features=r1 - r0)
+        sym["hdl"].barrier(channel=0)       # every rank's tiles have landed in this rank's buffer
+        return sym["buf"][turn, :M]

@@ -189,3 +189,25 @@ def test_linear4bit_default_is_nf4():
     assert float((y.float() - ref).abs().max() / ref.abs().max()) < TOL
     ref_fp = torch.nn.functional.linear(x.float(), w.float(), lin.bias.float())
     assert float((y.float() - ref_fp).abs().max() / ref_fp.abs().max()) < 0.15
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("M", [5, 48, 200])
+def test_scatter_epilogue_writes_every_output(bits, M):
+    """Column-parallel entry: the tile is written at column col0 of each output buffer (pitch ldy)
+    and nothing else in the buffers is touched."""
+    import quanta_b200 as Q
+    from quanta_b200.nn.functional import linear_wna16, linear_wna16_scatter
+    N, K, ldy, col0 = 384, 512, 1024, 256
+    g = torch.Generator().manual_seed(M + bits)
+    w = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    b = (torch.randn(N, generator=g) * 0.1).cuda().to(torch.bfloat16)
+    x = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    qf = Q.quantize_4bit(w, blocksize=64, packed=True) if bits == 4 else Q.quantize_8bit(w, blocksize=64)
+    ref = linear_wna16(x, *qf, b, bits=bits, blocksize=64, out_features=N)
+    outs = [torch.full((M, ldy), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    linear_wna16_scatter(x, *qf, b, ([o.data_ptr() for o in outs], ldy), col0, bits=bits, blocksize=64, out_features=N)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o[:, col0:col0 + N], ref)
+        assert bool((o[:, :col0] == 7.0).all()) and bool((o[:, col0 + N:] == 7.0).all())

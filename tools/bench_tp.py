@@ -6,7 +6,8 @@ Llama-3-70B-shaped weights on N GPUs of one box.  Launch:
 
 Every rank holds rows row_shard(out, N, rank, 128) of each weight.  Reports (rank 0, max over
 ranks, CUDA events): quantize GB/s aggregate (no collective on that path) and the TP linear
-(local fused kernel + one NCCL all-gather) in microseconds per call for M in {1,16,64,256}.
+(local fused kernel + one NCCL all-gather, and the kernel with the gather fused into its
+epilogue over symmetric memory) in microseconds per call for M in {1,16,64,256}.
 A small case is first checked against a single-device computation of the whole layer."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -56,6 +57,18 @@ for bits in (4, 8):
     err = float((y.float() - ref.float()).abs().max() / ref.float().abs().max())
     emit({"check": f"tp_linear W{bits}A16 == single device", "world": world, "bit_identical": same, "rel_err": err})
     assert err < 1e-2
+    if world > 1:
+        linf = TensorParallelLinear(K, N, bits=bits, bias=True, compute_dtype=torch.bfloat16, fused_gather=True)
+        linf.load_shard(w[r0:r1].to(dev), b[r0:r1].to(dev))
+        ok = True
+        for it in range(6):                                    # both buffers, several turns
+            xi = (x * (1 + it)).contiguous()
+            yf = linf(xi).clone()
+            refi = linear_wna16(xi, *qf, b.to(dev), bits=bits, blocksize=64, out_features=N)
+            ok = ok and bool(torch.equal(yf, refi))
+        emit({"check": f"tp_linear W{bits}A16 fused gather == single device", "world": world, "bit_identical": ok})
+        assert ok
+        del linf
 
 # ---- throughput on Llama-3-70B shapes ----
 SHAPES = [(8192, 8192), (1024, 8192), (28672, 8192), (8192, 28672)]
@@ -78,6 +91,10 @@ for (No, Ki) in SHAPES:
     for bits in (4, 8):
         lin = TensorParallelLinear(Ki, No, bits=bits, bias=False, compute_dtype=torch.bfloat16)
         lin.load_shard(wl)
+        linf = None
+        if world > 1:
+            linf = TensorParallelLinear(Ki, No, bits=bits, bias=False, compute_dtype=torch.bfloat16, fused_gather=True)
+            linf.qweight, linf.scale, linf.zero_point = lin.qweight, lin.scale, lin.zero_point
         for Mb in (1, 16, 64, 256):
             xb = torch.randn(Mb, Ki, device=dev).to(torch.bfloat16)
             for _ in range(3):
@@ -94,9 +111,39 @@ for (No, Ki) in SHAPES:
                 y = lin(xb)
             e1.record(); torch.cuda.synchronize()
             us = max_over_ranks(e0.elapsed_time(e1) * 1e3 / args.reps)
-            emit({"op": f"tp_linear W{bits}A16", "N": No, "K": Ki, "M": Mb, "world": world, "us": round(us, 2),
-                  "us_local_gemm": round(us_local, 2), "TFLOPs": round(2.0 * Mb * No * Ki / us / 1e6, 1)})
-        del lin
+            rec = {"op": f"tp_linear W{bits}A16", "N": No, "K": Ki, "M": Mb, "world": world, "us": round(us, 2),
+                   "us_local_gemm": round(us_local, 2), "TFLOPs": round(2.0 * Mb * No * Ki / us / 1e6, 1)}
+            if linf is not None:
+                for _ in range(3):
+                    linf(xb)
+                torch.cuda.synchronize(); dist.barrier()
+                e0.record()
+                for _ in range(args.reps):
+                    y = linf(xb)
+                e1.record(); torch.cuda.synchronize()
+                rec["us_fused"] = round(max_over_ranks(e0.elapsed_time(e1) * 1e3 / args.reps), 2)
+                # the same 20 calls replayed from a CUDA graph: device time without the host's launch path
+                for name, layer in (("us_graph", lin), ("us_fused_graph", linf)):
+                    try:
+                        side = torch.cuda.Stream()
+                        side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(side):
+                            layer(xb)
+                        torch.cuda.current_stream().wait_stream(side)
+                        torch.cuda.synchronize(); dist.barrier()
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr):
+                            for _ in range(args.reps):
+                                y = layer(xb)
+                        gr.replay(); torch.cuda.synchronize(); dist.barrier()
+                        e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+                        rec[name] = round(max_over_ranks(e0.elapsed_time(e1) * 1e3 / args.reps), 2)
+                        del gr
+                    except Exception as ex:                     # noqa: BLE001
+                        rec[name] = f"failed: {type(ex).__name__}: {str(ex)[:80]}"
+                        torch.cuda.synchronize()
+            emit(rec)
+        del lin, linf
     del wl, q4
     torch.cuda.empty_cache()
 if rank == 0 and args.out:
