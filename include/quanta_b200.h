@@ -64,7 +64,10 @@ QUANTA_API const char* quanta_error_string(int code);
  * (QUANTA_OP_GEMM: rows = M, cols = N;  QUANTA_OP_INT8_OUTLIER: rows = M,
  * cols = K).  Always >= 256.  The first 64 KB of the QUANTA_OP_GEMM workspace
  * hold arrival counters: they must be zero before the first call and every
- * call leaves them zero (allocate the buffer zero-filled, once).          */
+ * call leaves them zero (allocate the buffer zero-filled, once).  The same
+ * holds for the first 256 bytes of the QUANTA_OP_QUANTIZE_AFFINE /
+ * QUANTA_OP_BACKEND_QUANTIZE workspace (grid-barrier counters of the
+ * single-launch per-tensor kernel): keep that buffer for these entries only.  */
 QUANTA_API size_t quanta_workspace_bytes(int op, int64_t rows, int64_t cols);
 
 /* ---- convention A: Quanta/functional/quantization.py "linear" -------------

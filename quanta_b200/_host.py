@@ -39,6 +39,22 @@ def workspace(device, nbytes):
     return buf
 
 
+_quantize_workspaces = {}
+
+
+def quantize_workspace(device, nbytes):
+    """Per (device, stream) workspace of the quantize entries.  Its header holds the grid-barrier
+    counters of the single-launch per-tensor kernel, which must be zero before the first call and
+    are left zero by every call (include/quanta_b200.h): zero-initialised once, never shared with
+    other kernels' scratch."""
+    key = (device.index, stream_ptr(device))
+    buf = _quantize_workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _quantize_workspaces[key] = buf
+    return buf
+
+
 _gemm_workspaces = {}
 
 

@@ -42,7 +42,7 @@ def _quantize(tensor, per_channel, symmetric, bits):
         q = torch.empty(x.shape, dtype=torch.uint8, device=dev)
         scale = torch.empty(nparam, dtype=torch.float32, device=dev)
         zp = torch.empty(nparam, dtype=torch.float32, device=dev)
-        ws = _host.workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_BACKEND_QUANTIZE, rows if per_channel else 1,
+        ws = _host.quantize_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_BACKEND_QUANTIZE, rows if per_channel else 1,
                                                                     cols if per_channel else 1))
         st = _lib.lib().quanta_backend_quantize(x.data_ptr(), code, rows, cols, int(bool(per_channel)),
                                                 int(bool(symmetric)), bits, q.data_ptr(), scale.data_ptr(),

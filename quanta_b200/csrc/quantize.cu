@@ -11,6 +11,7 @@
 // common.cuh: affine_params / affine_quotient / code_bits).
 #include "common.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace quanta {
@@ -561,6 +562,291 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
 }
 
 // --------------------------------------------------------------------------
+// 2a. TENSOR mode in ONE launch: reduce, grid barrier, quantize from shared memory / L2
+// --------------------------------------------------------------------------
+// Per-tensor parameters need the global min/max before the first code can be written, so the
+// tensor is needed twice.  Two launches re-read all of it; here one persistent CTA per SM
+//   phase 1  streams its contiguous share of 16 KB tiles through shared memory for min/max and
+//            KEEPS the first R tiles there (R = all of them when the share fits: one HBM read),
+//   barrier  publishes its partial min/max, arrives at a grid-wide counter, waits for the others
+//            (all CTAs are resident: one per SM, grid <= #SMs, cooperative launch),
+//   phase 2  quantizes the resident tiles straight from shared memory while the producer warp
+//            re-streams the other tiles newest-first (they were loaded with L2 evict_last, so
+//            most of them are still in the 126 MB L2).
+// The counters live in the workspace header, which must be zero before the first call and is
+// left zero by every call (include/quanta_b200.h).
+constexpr int kFRows = 128;                       // rows per tile = threads per consumer group
+constexpr int kFGroups = 4;                       // consumer groups; a ring slot always belongs to one group
+constexpr int kFConsumers = kFRows * kFGroups;
+constexpr int kFThreads = kFConsumers + 32;
+constexpr int kFMaxSlots = 32;
+constexpr int kWsArriveIdx = 8, kWsDoneIdx = 9;   // grid-barrier counters (ints) in the workspace header
+
+template <typename T>
+__device__ __forceinline__ void load_row32(uint32_t row_addr, int r, float* v) {
+    using RL = RowLayout<T>;
+#pragma unroll
+    for (int j = 0; j < RL::kChunks; ++j) {
+        uint4 c = lds128(row_addr + (RL::swz(r, j) << 4));
+        if (sizeof(T) == 4) {
+            v[4 * j + 0] = __uint_as_float(c.x); v[4 * j + 1] = __uint_as_float(c.y);
+            v[4 * j + 2] = __uint_as_float(c.z); v[4 * j + 3] = __uint_as_float(c.w);
+        } else {
+            const T* e = reinterpret_cast<const T*>(&c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[8 * j + k] = to_f32(e[k]);
+        }
+    }
+}
+
+template <typename T, int BITS, bool PACK, int CONV>
+__global__ void __launch_bounds__(kFThreads, 1)
+quantize_tensor_fused_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ x, int64_t n,
+                             int64_t n_rows, int nslots, int ring_min, uint8_t* __restrict__ q_out,
+                             float* __restrict__ scale_out, float* __restrict__ zp_out, float* ws) {
+    using RL = RowLayout<T>;
+    constexpr int kTileBytes = kFRows * RL::kRowBytes;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kFMaxSlots], empty_bar[kFMaxSlots];
+    __shared__ float red_mn[kFConsumers / 32], red_mx[kFConsumers / 32];
+
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (int)((n_rows + kFRows - 1) / kFRows);
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+#ifdef QUANTA_FUSED_TRACE
+    long long tr[8]; unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    tr[0] = clock64();
+#define FTRACE(i) tr[i] = clock64()
+#else
+#define FTRACE(i) do { } while (0)
+#endif
+    const int t0 = (int)((int64_t)n_tiles * c / G), t1 = (int)((int64_t)n_tiles * (c + 1) / G);
+    const int cnt = t1 - t0;
+    const int R = cnt <= nslots ? cnt : nslots - ring_min;      // resident tiles
+    const int ns = cnt - R;                                     // streamed twice
+    const int ring = ns > 0 ? ring_min : kFGroups;              // multiple of kFGroups: slot -> group is fixed
+    const int K = ns < kFGroups ? ns : kFGroups;                // newest streamed tiles, kept in registers over the barrier
+
+    if (tid == 0) {
+        for (int s2 = 0; s2 < nslots; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], kFRows / 32); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kFConsumers / 32) {
+        // ===== producer: residents first, then the ring (phase 1 in order, phase 2 newest first) =====
+        if (lane == 0) {
+            prefetch_tensormap(&tmap);
+            const uint64_t pol_once = policy_evict_first(), pol_again = policy_evict_last();
+            for (int j = 0; j < R; ++j) {
+                mbar_arrive_expect_tx(&full_bar[j], kTileBytes);
+                tma_load_2d_addr(smem + j * kTileBytes, &tmap, smem_u32(&full_bar[j]), 0, (t0 + j) * kFRows, pol_once);
+            }
+            for (int m = 0; m < 2 * ns - K; ++m) {
+                const int u = m / ring, slot = R + (m - u * ring);
+                if (u > 0) mbar_wait(&empty_bar[slot], (uint32_t)((u & 1) ^ 1));
+                const int t = m < ns ? t0 + R + m : t1 - 1 - K - (m - ns);
+                mbar_arrive_expect_tx(&full_bar[slot], kTileBytes);
+                tma_load_2d_addr(smem + slot * kTileBytes, &tmap, smem_u32(&full_bar[slot]), 0, t * kFRows,
+                                 m < ns ? pol_again : pol_once);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: group g owns the items it can reach with a fixed slot -> group map =====
+    const int group = tid >> 7, r = tid & (kFRows - 1);
+    const uint32_t row_off = (uint32_t)r * RL::kRowBytes;
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    constexpr float Q = BITS == 8 ? 127.0f : 7.0f;
+
+    FTRACE(1);
+    // ---- phase 1: min / max ----
+    float m0[4], m1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m0[k] = __int_as_float(0x7f800000); m1[k] = __int_as_float(0xff800000); }
+    for (int i = group; i < R; i += kFGroups) {
+        mbar_wait(&full_bar[i], 0);
+        if ((int64_t)(t0 + i) * kFRows + r < n_rows) {
+            float v[kRowElems];
+            load_row32<T>(smem + i * kTileBytes + row_off, r, v);
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) { m0[k & 3] = min_nan(m0[k & 3], v[k]); m1[k & 3] = max_nan(m1[k & 3], v[k]); }
+        }
+    }
+    // ring use m is consumed by group (R + m) % kFGroups
+    const int mfirst = (group - R % kFGroups + kFGroups) % kFGroups;
+    // The row of the group's LAST streamed tile stays in `vk` across the grid barrier: the K newest
+    // tiles (one per group) are quantized from registers and never fetched again.
+    float vk[kRowElems];
+#pragma unroll
+    for (int k = 0; k < kRowElems; ++k) vk[k] = 0.0f;
+    int keep_m = -1;
+    for (int m = mfirst; m < ns; m += kFGroups) {
+        const int u = m / ring, slot = R + (m - u * ring);
+        mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
+        load_row32<T>(smem + slot * kTileBytes + row_off, r, vk);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        if ((int64_t)(t0 + R + m) * kFRows + r < n_rows) {
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) { m0[k & 3] = min_nan(m0[k & 3], vk[k]); m1[k & 3] = max_nan(m1[k & 3], vk[k]); }
+        }
+        keep_m = m;
+    }
+    float mn = min_nan(min_nan(m0[0], m0[1]), min_nan(m0[2], m0[3]));
+    float mx = max_nan(max_nan(m1[0], m1[1]), max_nan(m1[2], m1[3]));
+    // elements past the last full 32-element row (the tail kernel quantizes them)
+    if (c == 0) {
+        const int64_t j = n_rows * kRowElems + tid;
+        if (j < n) { const float f = to_f32(x[j]); mn = min_nan(mn, f); mx = max_nan(mx, f); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { red_mn[warp] = mn; red_mx[warp] = mx; }
+    asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
+
+    FTRACE(2);
+    // ---- grid barrier: warp 0 publishes the CTA's partial, waits for all CTAs, reduces their partials ----
+    float* pmin = ws + kWsHeaderFloats + 64;
+    float* pmax = pmin + kMaxPartialCtas;
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(ws) + kWsArriveIdx;
+    unsigned int* done = reinterpret_cast<unsigned int*>(ws) + kWsDoneIdx;
+    if (warp == 0) {
+        mn = red_mn[lane & (kFConsumers / 32 - 1)]; mx = red_mx[lane & (kFConsumers / 32 - 1)];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) {
+            pmin[c] = mn; pmax[c] = mx;
+            // release: the partial above is visible to whoever observes the incremented counter
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(arrive) : "memory");
+            unsigned int seen = 0, spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+                if (seen >= (unsigned int)G) break;
+                if (++spins > (1u << 26)) __trap();    // workspace header was not zero, or the grid is not co-resident
+            }
+        }
+        __syncwarp();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        float v0[5], v1[5];                            // G <= 148 partials: 5 per lane, all loads in flight at once
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int idx = lane + 32 * k;
+            v0[k] = __ldcg(pmin + (idx < G ? idx : 0));
+            v1[k] = __ldcg(pmax + (idx < G ? idx : 0));
+        }
+        mn = v0[0]; mx = v1[0];
+#pragma unroll
+        for (int k = 1; k < 5; ++k) { mn = min_nan(mn, v0[k]); mx = max_nan(mx, v1[k]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) {
+            red_mn[0] = mn; red_mx[0] = mx;
+            // every partial has been read by this CTA; the last CTA through leaves the counters zero
+            const unsigned int old = atomicAdd(done, 1u);
+            if (old == (unsigned int)(G - 1)) { *arrive = 0u; *done = 0u; }
+        }
+    }
+    FTRACE(3);
+    asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
+    mn = red_mn[0]; mx = red_mx[0];
+
+    ElemParams gp{0.f, 1.f, 0.f};
+    float sc, z, rr; bool close;
+    group_params<CONV>(mn, mx, BITS, &sc, &z, &rr, &close);
+    const bool early = (CONV != kConvA) && close;
+    if (early) { sc = 1.0f; z = mn; }                     // cpu/quantization.py:38-39
+    gp.s = sc; gp.a = z; gp.r = rr;
+    if (c == 0 && tid == 0) {                             // publish for the caller and the tail kernel
+        scale_out[0] = sc; zp_out[0] = z;
+        ws[kWsHeaderFloats] = rr;
+        reinterpret_cast<int*>(ws)[0] = early ? 1 : 0;
+    }
+
+    // ---- phase 2: codes ----
+    auto quantize_row = [&](const float* v, int t) {
+        const int64_t grow = (int64_t)t * kFRows + r;
+        if (grow >= n_rows) return;
+        uint32_t u[kRowElems];
+        if (CONV == kConvA && gp.r != 0.0f) {
+            const float nscale = -gp.s;
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) {
+                const float a = __fsub_rn(v[k], gp.a);
+                const float q0 = __fmul_rn(a, gp.r);
+                const float rem = __fmaf_rn(nscale, q0, a);
+                // rcp != 0: the range is finite, every x lies in [min, max] and the quotient in
+                // [0, L + eps] — the clamp of code_bits is a no-op
+                u[k] = __float_as_uint(__fadd_rn(__fmaf_rn(gp.r, rem, q0), kMagic));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kRowElems; ++k) u[k] = elem_code_bits<CONV, false>(v[k], gp, L, Q);
+        }
+        if (BITS == 4 && PACK) {
+            uint4 o;
+            o.x = pack_nibbles8<CONV>(u + 0);  o.y = pack_nibbles8<CONV>(u + 8);
+            o.z = pack_nibbles8<CONV>(u + 16); o.w = pack_nibbles8<CONV>(u + 24);
+            if (early) o = make_uint4(0, 0, 0, 0);
+            __stcs(reinterpret_cast<uint4*>(q_out + grow * 16), o);
+        } else {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = early ? 0u : pack_bytes4<CONV, BITS>(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+            uint4* dst = reinterpret_cast<uint4*>(q_out + grow * 32);
+            __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+            __stcs(dst + 1, make_uint4(w[4], w[5], w[6], w[7]));
+        }
+    };
+    FTRACE(4);
+    if (keep_m >= ns - K && keep_m >= 0) quantize_row(vk, t0 + R + keep_m);       // from registers
+    FTRACE(5);
+    // resident tiles (shared memory) and re-streamed tiles (L2, newest first) alternate, so the L2
+    // latency of the ring hides behind the resident tiles' arithmetic.  Phase-2 ring uses continue the
+    // numbering: use m = ns + k re-reads tile t1 - 1 - K - k.
+    const int m_end = 2 * ns - K;
+    int i2 = group;
+    int m2 = ns + ((group - (R + ns) % kFGroups + kFGroups) % kFGroups);
+    while (i2 < R || m2 < m_end) {
+        if (i2 < R) {
+            float v[kRowElems];
+            load_row32<T>(smem + i2 * kTileBytes + row_off, r, v);
+            quantize_row(v, t0 + i2);
+            i2 += kFGroups;
+        }
+        if (m2 < m_end) {
+            const int u = m2 / ring, slot = R + (m2 - u * ring);
+            mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
+            float v[kRowElems];
+            load_row32<T>(smem + slot * kTileBytes + row_off, r, v);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);          // refill while we compute
+            quantize_row(v, t1 - 1 - K - (m2 - ns));
+            m2 += kFGroups;
+        }
+    }
+#ifdef QUANTA_FUSED_TRACE
+    FTRACE(6);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (tid == 0 && (c == 0 || c == G - 1))
+        printf("cta %d cnt %d R %d ns %d: init %lld ph1 %lld arrive+spin %lld reduce %lld resident %lld streamed %lld | total %lld cyc, %llu ns (start %llu)\n",
+               c, cnt, R, ns, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[6] - tr[0], g1 - g0, g0);
+#endif
+}
+
+// --------------------------------------------------------------------------
 // 2b. the same stream over SEVERAL tensors in one launch (blockwise, convention A)
 // --------------------------------------------------------------------------
 // Quantizing a model is hundreds of independent matrices; one launch per matrix pays a
@@ -927,6 +1213,53 @@ static int launch_rows_tma(const T* x, int64_t n_rows, int lanes_per_block, uint
     return launch_rows_tma_impl<T, BITS, PACK, CONV, BLOCKWISE, false>(tmap, n_rows, lanes_per_block, q, scale, zp, ws, nparts, st);
 }
 
+static bool use_fused_tensor() {
+    static const bool v = []() {
+        const char* e = getenv("QUANTA_B200_TWO_PASS");          // escape hatch: separate reduce + quantize launches
+        return !(e && e[0] == '1');
+    }();
+    return v;
+}
+
+// One cooperative launch: a CTA per SM (or per tile when there are fewer tiles).
+template <typename T, int BITS, bool PACK, int CONV>
+static int launch_tensor_fused(const T* x, int64_t n, int64_t n_rows, uint8_t* q, float* scale, float* zp, float* ws,
+                               cudaStream_t st) {
+    using RL = RowLayout<T>;
+    constexpr int kTileBytes = kFRows * RL::kRowBytes;
+    CUtensorMap tmap;
+    int rc = make_tensor_map_2d(&tmap, TmaType<T>::v, sizeof(T), x, kRowElems, (uint64_t)n_rows, RL::kRowBytes,
+                                kRowElems, kFRows,
+                                sizeof(T) == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    auto kern = quantize_tensor_fused_kernel<T, BITS, PACK, CONV>;
+    int nslots = (224 * 1024) / kTileBytes;                      // 14 x 16 KB (+1 KB alignment) of the 227 KB an SM offers
+    if (nslots > kFMaxSlots) nslots = kFMaxSlots;
+    int ring_min = (64 * 1024) / kTileBytes;                     // 64 KB in flight per SM
+    if (const char* e = getenv("QUANTA_B200_FUSED_RING")) { int v = atoi(e); if (v >= kFGroups && v < nslots) ring_min = v; }
+    ring_min = (ring_min + kFGroups - 1) / kFGroups * kFGroups;
+    const int smem = nslots * kTileBytes + 1024;
+    static bool attr_set = false;      // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int64_t n_tiles = (n_rows + kFRows - 1) / kFRows;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs));
+    cfg.blockDim = dim3(kFThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;                 // the grid barrier needs every CTA resident
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (const char* e = getenv("QUANTA_B200_FUSED_COOP")) { if (atoi(e) == 0) cfg.numAttrs = 0; }
+    return cuda_status(cudaLaunchKernelEx(&cfg, kern, tmap, x, n, n_rows, nslots, ring_min, q, scale, zp, ws));
+}
+
 static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -941,8 +1274,19 @@ static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, ui
         int64_t want = (n + 256 * 16 - 1) / (256 * 16);
         const int cap = kNumSMs * 4;                       // 4 resident CTAs of 256 threads per SM
         int g = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-        minmax_tensor_partial_kernel<T><<<g, 256, 0, st>>>(x, n, pmin, pmax);
         int64_t n_rows = aligned16(x) && aligned16(q) ? n / kRowElems : 0;
+        if (n_rows > 0 && use_fused_tensor()) {
+            int rc = launch_tensor_fused<T, BITS, PACK, CONV>(x, n, n_rows, q, scale, zp, ws, st);
+            if (rc) return rc;
+            const int64_t start = n_rows * kRowElems;
+            if (start < n) {
+                int64_t pairs = (n - start + 1) / 2;
+                quantize_generic_kernel<T, BITS, PACK, CONV><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+                    x, start, n, 1, q, scale, zp, ws);
+            }
+            return cuda_status(cudaGetLastError());
+        }
+        minmax_tensor_partial_kernel<T><<<g, 256, 0, st>>>(x, n, pmin, pmax);
         if (n_rows > 0) {
             // the streaming kernel finalizes the reduction itself and publishes scale / zp
             int rc = launch_rows_tma<T, BITS, PACK, CONV, false>(x, n_rows, 1, q, scale, zp, ws, g, st);

@@ -56,7 +56,7 @@ def _quantize_linear(tensor, bits, per_channel, blocksize, packed):
         # only the two-pass modes need scratch: per-tensor partials, or per-column partials for dim 0
         ws_bytes = _lib.lib().quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, rows if mode == _lib.MODE_DIM0 else 1,
                                                      cols if mode == _lib.MODE_DIM0 else 1)
-        ws = _host.workspace(dev, ws_bytes)
+        ws = _host.quantize_workspace(dev, ws_bytes)
         st = _lib.lib().quanta_quantize_affine(x.data_ptr(), code, rows, cols, mode, B, bits, int(bool(packed)),
                                                q.data_ptr(), scale.data_ptr(), zp.data_ptr(),
                                                ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
