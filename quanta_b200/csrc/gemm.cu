@@ -187,9 +187,11 @@ __constant__ float kGemmNf4Levels[16] = {
     0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
 
 constexpr int kMaxOut = 8;
+// NOUT = 1 for the plain GEMM (one map, compile-time loops), kMaxOut for the scatter entry
+template <int NOUT>
 struct GemmOutputs {
-    CUtensorMap maps[kMaxOut];      // TMA-store maps of the output buffers ([M, col0 + N] windows, pitch ldy)
-    void* y[kMaxOut];
+    CUtensorMap maps[NOUT];         // TMA-store maps of the output buffers ([M, col0 + N] windows, pitch ldy)
+    void* y[NOUT];
 };
 
 struct GemmParams {
@@ -332,11 +334,70 @@ __device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* map,
     }
 }
 
-template <typename ACT, int BITS, int CG>
+// Stream-K fix-up of one tile by `nthreads` threads (thread j): sum the fp32 partials of every
+// contributing CTA in a fixed order (deterministic), add the bias, write y.  Thread -> 4 consecutive
+// features, rows j/32, j/32 + nthreads/32, ...; kFixRows rows (float4 each) in flight per contributor.
+constexpr int kFixRows = 6;
+template <typename ACT, int CG, int NOUT>
+__device__ __noinline__ void fixup_reduce(const GemmParams& p, const GemmOutputs<NOUT>& outs, const ACT* __restrict__ bias,
+                                             const float* __restrict__ partial, int tile, int crank, int j, int nthreads) {
+    using AT = ActTraits<ACT>;
+    const int n_tile = (tile % p.n_tiles) * CG + crank, m_tile = tile / p.n_tiles;
+    const int m0 = m_tile * p.mb;
+    const int m_valid = min(p.mb, p.M - m0);
+    const int f4 = 4 * (j & 31), mq = j >> 5, mstep = nthreads >> 5;
+    const int gn4 = n_tile * kTileN + f4;
+    float b4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? AT::to_float(bias[gn4 + e]) : 0.0f;
+    const bool vec_ok = p.vec_store && gn4 + 3 < p.N;
+    const unsigned int tu0 = (unsigned int)tile * (unsigned int)p.S;
+    const int c_first = cta_of_unit(tu0, p), c_last = cta_of_unit(tu0 + (unsigned int)p.S - 1u, p);
+    const size_t slot_elems = (size_t)(kTileN * p.mb);
+    for (int mb0 = mq; mb0 < m_valid; mb0 += kFixRows * mstep) {
+        float4 acc[kFixRows];
+#pragma unroll
+        for (int i = 0; i < kFixRows; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = c_first; c <= c_last; ++c) {
+            const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / (unsigned int)p.S)) ? 0 : 1;
+            const float* src = partial + (((size_t)c * 2 + wc) * CG + crank) * slot_elems + f4;
+            float4 v[kFixRows];
+#pragma unroll
+            for (int i = 0; i < kFixRows; ++i) {
+                const int m = mb0 + mstep * i;
+                v[i] = (m < m_valid) ? __ldcg(reinterpret_cast<const float4*>(src + m * kTileN))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < kFixRows; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+        }
+#pragma unroll
+        for (int i = 0; i < kFixRows; ++i) {
+            const int m = mb0 + mstep * i;
+            if (m < m_valid) {
+                const float o[4] = {acc[i].x + b4[0], acc[i].y + b4[1], acc[i].z + b4[2], acc[i].w + b4[3]};
+                for (int ob = 0; ob < (NOUT == 1 ? 1 : p.n_out); ++ob) {
+                    ACT* dst = static_cast<ACT*>(outs.y[ob]) + (int64_t)(m0 + m) * p.ldy + p.col0 + gn4;
+                    if (vec_ok) {
+                        uint2 pk;
+                        pk.x = AT::pack(o[0], o[1]);
+                        pk.y = AT::pack(o[2], o[3]);
+                        *reinterpret_cast<uint2*>(dst) = pk;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename ACT, int BITS, int CG, int NOUT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_z,
-                  const __grid_constant__ GemmOutputs outs, const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
+                  const __grid_constant__ GemmOutputs<NOUT> outs, const float* __restrict__ scale, const float* __restrict__ zp, const ACT* __restrict__ bias,
                   unsigned int* __restrict__ counters, float* __restrict__ partial,
                   const __grid_constant__ GemmParams p) {
     using AT = ActTraits<ACT>;
@@ -345,6 +406,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     __shared__ uint64_t a_full[kDqGroups], a_empty[kDqGroups], d_full[2], d_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int fix_flag;
+    __shared__ int fin_tile;            // tile whose stream-K fix-up is done by the whole CTA at the end (-1: none)
     __shared__ __align__(1024) float stage[16][kTileN];        // epilogue transpose buffer (8 KB)
     __shared__ uint32_t nf4_pairs[256];                        // NF4: byte -> (level[lo nibble], level[hi nibble]) in the act type
 #ifdef QUANTA_GEMM_TRACE
@@ -376,6 +438,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     SegWalk walk;
     walk.init(p, cta);
     int tile, s0, s1;
+    if (tid == 32 * kFirstEpiWarp) fin_tile = -1;       // before the CTA-wide barrier below
     if (BITS == 4 && p.nf4 && tid >= 32 * kFirstDqWarp && tid < 32 * kFirstDqWarp + 256) {
         const int b = tid - 32 * kFirstDqWarp;      // visible to the dequant warps after the CTA-wide barrier below
         nf4_pairs[b] = AT::pack(kGemmNf4Levels[b & 15], kGemmNf4Levels[b >> 4]);
@@ -543,7 +606,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int quarter = warp & 3;
         const int row = 32 * quarter + lane;
         const int etid = tid - 32 * kFirstEpiWarp;
-        if (etid == 0 && p.y_tma) { for (int o = 0; o < p.n_out; ++o) prefetch_tensormap(&outs.maps[o]); }
+        if (etid == 0 && p.y_tma) { for (int o = 0; o < (NOUT == 1 ? 1 : p.n_out); ++o) prefetch_tensormap(&outs.maps[o]); }
         int seg = 0, esc = 0;                 // esc: CTA-wide stage counter at the start of the segment
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
@@ -553,6 +616,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const bool n_ok = gn < p.N;
             const int m_valid = min(p.mb, p.M - m0);
             const bool whole = (s0 == 0 && s1 == p.S);
+            const bool last_seg = walk.u >= walk.u1;                  // no further segment for this CTA
             const float b = (bias != nullptr && n_ok) ? AT::to_float(bias[gn]) : 0.0f;
             // this CTA's partial slot for the tile: 0 if the tile is the first one the CTA touches, else 1
             const unsigned int u_first = p.U * cta / (unsigned int)p.G;
@@ -610,7 +674,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                     if (etid == 0 && c0 < m_valid) {
                         // one store per output buffer: the local y, or every tensor-parallel peer's y over NVLink
-                        for (int o = 0; o < p.n_out; ++o)
+                        for (int o = 0; o < (NOUT == 1 ? 1 : p.n_out); ++o)
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                          ::"l"(reinterpret_cast<uint64_t>(&outs.maps[o])), "r"(smem_u32(sbuf)),
                                            "r"(p.col0 + n_tile * kTileN), "r"(m0 + c0) : "memory");
@@ -633,7 +697,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             const float4 v = *reinterpret_cast<const float4*>(&stage[ml][f4]);
                             if (whole) {
                                 const float o[4] = {v.x + b4[0], v.y + b4[1], v.z + b4[2], v.w + b4[3]};
-                                for (int ob = 0; ob < p.n_out; ++ob) {
+                                for (int ob = 0; ob < (NOUT == 1 ? 1 : p.n_out); ++ob) {
                                     ACT* dst = static_cast<ACT*>(outs.y[ob]) + (int64_t)(m0 + m) * p.ldy + p.col0 + gn4;
                                     if (vec_ok) {
                                         uint2 pk;
@@ -674,45 +738,12 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (fix_flag) {
-                    // thread -> 4 consecutive features, every 4th batch row; 4 rows x all contributors in flight
-                    const int mq = etid >> 5;
-                    const size_t slot_elems = (size_t)(kTileN * p.mb);
-                    for (int mb0 = mq; mb0 < m_valid; mb0 += 32) {
-                        float4 acc[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int c = c_first; c <= c_last; ++c) {
-                            const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / (unsigned int)p.S)) ? 0 : 1;
-                            const float* src = partial + (((size_t)c * 2 + wc) * CG + crank) * slot_elems + f4;
-                            float4 v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int m = mb0 + 4 * i;
-                                v[i] = (m < m_valid) ? __ldcg(reinterpret_cast<const float4*>(src + m * kTileN))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int m = mb0 + 4 * i;
-                            if (m < m_valid) {
-                                const float o[4] = {acc[i].x + b4[0], acc[i].y + b4[1], acc[i].z + b4[2], acc[i].w + b4[3]};
-                                for (int ob = 0; ob < p.n_out; ++ob) {
-                                    ACT* dst = static_cast<ACT*>(outs.y[ob]) + (int64_t)(m0 + m) * p.ldy + p.col0 + gn4;
-                                    if (vec_ok) {
-                                        uint2 pk;
-                                        pk.x = AT::pack(o[0], o[1]);
-                                        pk.y = AT::pack(o[2], o[3]);
-                                        *reinterpret_cast<uint2*>(dst) = pk;
-                                    } else {
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = AT::from_float(o[e]);
-                                    }
-                                }
-                            }
-                        }
+                    if (last_seg && p.mb >= 64) {
+                        // the CTA has nothing left to do: hand the reduction to all 20 epilogue + dequant
+                        // warps (5x the loads in flight) after the role loops
+                        if (etid == 0) fin_tile = tile;
+                    } else {
+                        fixup_reduce<ACT, CG, NOUT>(p, outs, bias, partial, tile, (int)crank, etid, 32 * kEpiWarps);
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // fix_flag is reused
@@ -849,6 +880,14 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     }
 
+    if (warp >= kFirstEpiWarp && p.mb >= 64) {
+        // epilogue + dequant warps: a pending last-segment fix-up is reduced by all of them (small
+        // batches have too few rows to share: the epilogue warps did it in their loop)
+        asm volatile("bar.sync 3, %0;" ::"n"(32 * (kEpiWarps + kDqWarps)) : "memory");
+        const int ft = *reinterpret_cast<volatile int*>(&fin_tile);
+        if (ft >= 0)
+            fixup_reduce<ACT, CG, NOUT>(p, outs, bias, partial, ft, (int)crank, tid - 32 * kFirstEpiWarp, 32 * (kEpiWarps + kDqWarps));
+    }
     if (tid == 32 * kFirstEpiWarp) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // y stores have landed
     tc_fence_before();
     __syncthreads();
@@ -888,6 +927,10 @@ static int choose_units(int tiles, int S, int mb, int raw_bytes, int cg) {
         if (G != tiles) {
             const double contributors = (double)G / tiles < 2.0 ? 2.0 : (double)G / tiles + 1.0;
             cost += 4000.0 + 2.0 * tile_io * (1.0 + contributors);
+            // ranges that do not coincide with tile boundaries give most CTAs TWO partial tiles (two
+            // accumulator drains and partial stores, uneven contributor counts): measured ~6 tile
+            // transfers slower than the tile-aligned split on 4096 x 14336 at M = 64 / 128 / 256
+            if (G % tiles != 0) cost += 6.0 * tile_io;
         }
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
     };
@@ -904,7 +947,7 @@ size_t gemm_workspace_bytes(int64_t M, int64_t) {
     return (size_t)kCounterBytes + (size_t)kNumSMs * 2 * kTileN * (size_t)mb * sizeof(float) + 512;
 }
 
-template <typename ACT, int BITS, int CG>
+template <typename ACT, int BITS, int CG, int NOUT>
 static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const float* scale, const float* zp,
                           const ACT* bias, void* const* ys, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
                           cudaStream_t st) {
@@ -955,9 +998,9 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
                                 (uint64_t)p.scale_stride * 4, kKbPerStage, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
-    GemmOutputs outs;
+    GemmOutputs<NOUT> outs;
     bool aligned16 = true, aligned8 = true;
-    for (int o = 0; o < kMaxOut; ++o) {
+    for (int o = 0; o < NOUT; ++o) {
         outs.maps[o] = tmap_w;                              // placeholder
         outs.y[o] = o < p.n_out ? ys[o] : nullptr;
         if (o < p.n_out) {
@@ -976,7 +1019,7 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
             if (rc) return rc;
         }
     }
-    auto kern = gemm_wna16_kernel<ACT, BITS, CG>;
+    auto kern = gemm_wna16_kernel<ACT, BITS, CG, NOUT>;
     const int smem = (int)(p.x_ring_off + (uint32_t)p.x_stages * p.x_slot_bytes + 1024);
     static int smem_set = 0;           // per instantiation
     if (smem > smem_set) {             // static __shared__ (barriers) also counts against the 227 KB opt-in limit
@@ -1051,8 +1094,12 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     p.block_shift = bs;
     p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
               ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
-    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
-    return gemm_launch_cg<ACT, BITS, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+    if (n_out > 1) {
+        if (cg == 2) return gemm_launch_cg<ACT, BITS, 2, kMaxOut>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+        return gemm_launch_cg<ACT, BITS, 1, kMaxOut>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+    }
+    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+    return gemm_launch_cg<ACT, BITS, 1, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
 }
 
 }  // namespace quanta

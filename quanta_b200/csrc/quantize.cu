@@ -847,6 +847,358 @@ quantize_tensor_fused_kernel(const __grid_constant__ CUtensorMap tmap, const T* 
 }
 
 // --------------------------------------------------------------------------
+// 2a'. DIM0 mode (per_channel=True, convention A) in ONE launch
+// --------------------------------------------------------------------------
+// Same skeleton as the per-tensor kernel, over 2-D tiles of the matrix: a tile is [128 rows x 32
+// columns], tiles are numbered down the rows of a 32-column strip first, and a CTA's contiguous
+// tile range touches a few strips.  Phase 1 reduces columns (lane = column, a warp walks 32 rows:
+// conflict-free under the TMA swizzle) into per-strip tables in shared memory and publishes them;
+// after the grid barrier every CTA combines, for each of ITS strips, the partials of the CTAs that
+// share the strip, derives the 32 columns' parameters once into shared memory, and phase 2
+// quantizes row-per-thread with broadcast parameter reads.
+constexpr int kD0MaxStrips = 16;                 // strips per CTA the shared parameter table can hold
+constexpr int kD0SlotFloats = 64;                // one partial: 32 column minima + 32 maxima (as ordered keys)
+
+// float <-> unsigned key whose integer order is the float order (-0.0 < +0.0); NaN maps to the
+// extreme that wins the reduction, so min/max propagate NaN like torch.min / torch.max
+__device__ __forceinline__ uint32_t key_of(float f, bool for_min) {
+    const uint32_t b = __float_as_uint(f);
+    if (f != f) return for_min ? 0u : 0xFFFFFFFFu;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_of_key(uint32_t k) {
+    if (k == 0u || k == 0xFFFFFFFFu) return __int_as_float(0x7fc00000);        // only NaN maps there
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+struct Dim0Geom {
+    int tps;            // tiles per strip = ceil(rows / 128)
+    int n_tiles;
+    int max_strips;     // partial slots per CTA
+};
+// first tile of CTA c: floor(n_tiles * c / G) in 32-bit arithmetic (tq = n_tiles / G, trem = n_tiles % G)
+struct Dim0Split { int G, tq, trem; };
+__device__ __forceinline__ int d0_first_tile(int c, const Dim0Split& sp) { return sp.tq * c + (sp.trem * c) / sp.G; }
+__device__ __forceinline__ int d0_cta_of_tile(int t, const Dim0Split& sp) {
+    int c = sp.tq > 0 ? t / (sp.tq + 1) : 0;             // never above the answer: first_tile(c) <= (tq + 1) * c
+    if (c > sp.G - 1) c = sp.G - 1;
+    while (c + 1 < sp.G && d0_first_tile(c + 1, sp) <= t) ++c;
+    return c;
+}
+
+// 4 consecutive columns (quad cq) of tile row `row`
+template <typename T>
+__device__ __forceinline__ void d0_load4(uint32_t tile_addr, int row, int cq, float* f) {
+    using RL = RowLayout<T>;
+    if (sizeof(T) == 4) {
+        const uint4 v = lds128(tile_addr + (uint32_t)row * RL::kRowBytes + ((uint32_t)RL::swz(row, cq) << 4));
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    } else {
+        uint2 v;
+        const uint32_t a = tile_addr + (uint32_t)row * RL::kRowBytes + ((uint32_t)RL::swz(row, cq >> 1) << 4) + (uint32_t)(cq & 1) * 8u;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+        const T* e2 = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = to_f32(e2[j]);
+    }
+}
+template <int BITS, bool PACK>
+__device__ __forceinline__ void d0_stage4(uint32_t stage, int row, int cq, const uint32_t* u) {
+    if (BITS == 4 && PACK) {
+        const uint32_t h = (((u[3] * 16u + u[2]) * 16u + u[1]) * 16u + u[0]) - kMagicBits * 0x1111u;
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(stage + (uint32_t)row * 16u + (uint32_t)cq * 2u), "h"((unsigned short)h) : "memory");
+    } else {
+        const uint32_t w = pack_bytes4<kConvA, BITS>(u[0], u[1], u[2], u[3]);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stage + (uint32_t)row * 32u + (uint32_t)cq * 4u), "r"(w) : "memory");
+    }
+}
+// rare: a tile with a column whose scale is outside [2^-60, 2^60] (constant-zero columns, inf/NaN):
+// generic arithmetic with true divides, out of line (scalar arguments only, so nothing of the hot path
+// is forced into local memory)
+template <typename T, int BITS, bool PACK>
+__device__ __noinline__ void d0_tile_slow(uint32_t tile_addr, uint32_t stage, int row_base, int cq, float4 a4, float4 s4,
+                                          float4 r4) {
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    const ElemParams ep[4] = {{a4.x, s4.x, r4.x}, {a4.y, s4.y, r4.y}, {a4.z, s4.z, r4.z}, {a4.w, s4.w, r4.w}};
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int row = row_base + 4 * i;
+        float f[4];
+        d0_load4<T>(tile_addr, row, cq, f);
+        uint32_t u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = elem_code_bits<kConvA>(f[j], ep[j], L, 0.0f);
+        d0_stage4<BITS, PACK>(stage, row, cq, u);
+    }
+}
+
+template <typename T, int BITS, bool PACK>
+__global__ void __launch_bounds__(kFThreads, 1)
+quantize_dim0_fused_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows, int64_t cols, Dim0Geom geo,
+                           int nslots, int ring_min, uint8_t* __restrict__ q_out, float* __restrict__ scale_out,
+                           float* __restrict__ zp_out, float* ws) {
+    using RL = RowLayout<T>;
+    constexpr int kTileBytes = kFRows * RL::kRowBytes;
+    constexpr float L = BITS == 8 ? 255.0f : 15.0f;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kFMaxSlots], empty_bar[kFMaxSlots];
+    __shared__ uint32_t skey[kD0MaxStrips][2][32];                 // per local strip: column min / max keys
+    __shared__ __align__(16) float sparam[kD0MaxStrips][3][32];    // per strip: zero point (min) | scale | rcp of 32 columns
+
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+    const int n_tiles = geo.n_tiles, tps = geo.tps;
+#ifdef QUANTA_FUSED_TRACE
+    long long tr[8];
+    tr[0] = clock64();
+#endif
+    const Dim0Split sp{G, n_tiles / G, n_tiles % G};
+    const int t0 = d0_first_tile(c, sp), t1 = d0_first_tile(c + 1, sp);
+    const int cnt = t1 - t0;
+    const int R = cnt <= nslots ? cnt : nslots - ring_min;
+    const int ns = cnt - R;
+    const int ring = ns > 0 ? ring_min : kFGroups;
+    constexpr int K = 0;                        // no register-held tiles here (keeps phase 2 to ONE inlined tile body)
+    const int s_first = t0 / tps;
+    const int nls = (t1 - 1) / tps - s_first + 1;                  // local strips of this CTA (<= geo.max_strips)
+
+    if (tid == 0) {
+        for (int s2 = 0; s2 < nslots; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], kFRows / 32); }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < nls * 32; i += kFThreads) { skey[i >> 5][0][i & 31] = 0xFFFFFFFFu; skey[i >> 5][1][i & 31] = 0u; }
+    __syncthreads();
+
+    if (warp == kFConsumers / 32) {
+        if (lane == 0) {
+            prefetch_tensormap(&tmap);
+            const uint64_t pol_once = policy_evict_first(), pol_again = policy_evict_last();
+            auto load = [&](int slot, int t, uint64_t pol) {
+                const int strip = t / tps, rb = t - strip * tps;
+                mbar_arrive_expect_tx(&full_bar[slot], kTileBytes);
+                tma_load_2d_addr(smem + slot * kTileBytes, &tmap, smem_u32(&full_bar[slot]), strip * kRowElems, rb * kFRows, pol);
+            };
+            for (int j = 0; j < R; ++j) load(j, t0 + j, pol_once);
+            for (int m = 0; m < 2 * ns - K; ++m) {
+                const int u = m / ring, slot = R + (m - u * ring);
+                if (u > 0) mbar_wait(&empty_bar[slot], (uint32_t)((u & 1) ^ 1));
+                load(slot, m < ns ? t0 + R + m : t1 - 1 - K - (m - ns), m < ns ? pol_again : pol_once);
+            }
+        }
+        return;
+    }
+
+    const int group = tid >> 7, r = tid & (kFRows - 1), gw = (tid >> 5) & 3;       // gw: warp within the group
+    // Thread mapping of both phases: lane = (column quad cq, row phase rp); in step i the warp covers rows
+    // 32*gw + 4*i + rp, i = 0..7 — one 16-byte chunk per lane, 8 lanes per 128-byte tile row: conflict-free
+    // under the TMA swizzle, and a thread only ever needs the parameters of ITS 4 columns.
+    const int cq = lane & 7, rp = lane >> 3;
+    auto load4 = [&](uint32_t tile_addr, int row, float* f) { d0_load4<T>(tile_addr, row, cq, f); };
+
+    // ---- phase 1: column min / max ----
+    float cmn[4], cmx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cmn[j] = __int_as_float(0x7f800000); cmx[j] = __int_as_float(0xff800000); }
+    int cur_ls = -1;
+    auto flush = [&]() {
+        if (cur_ls >= 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicMin(&skey[cur_ls][0][4 * cq + j], key_of(cmn[j], true));
+                atomicMax(&skey[cur_ls][1][4 * cq + j], key_of(cmx[j], false));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cmn[j] = __int_as_float(0x7f800000); cmx[j] = __int_as_float(0xff800000); }
+    };
+    auto reduce_tile = [&](uint32_t tile_addr, int t) {
+        const int strip = t / tps, rb = t - strip * tps;
+        if (strip - s_first != cur_ls) { flush(); cur_ls = strip - s_first; }
+        const int64_t row0 = (int64_t)rb * kFRows;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 32 * gw + 4 * i + rp;
+            float f[4];
+            load4(tile_addr, row, f);
+            if (row0 + row < rows) {                               // rows past the end are TMA zero fill
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { cmn[j] = min_nan(cmn[j], f[j]); cmx[j] = max_nan(cmx[j], f[j]); }
+            }
+        }
+    };
+    for (int i = group; i < R; i += kFGroups) {
+        mbar_wait(&full_bar[i], 0);
+        reduce_tile(smem + i * kTileBytes, t0 + i);
+    }
+    const int mfirst = (group - R % kFGroups + kFGroups) % kFGroups;
+    for (int m = mfirst; m < ns; m += kFGroups) {
+        const int u = m / ring, slot = R + (m - u * ring);
+        mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
+        reduce_tile(smem + slot * kTileBytes, t0 + R + m);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+    }
+    flush();
+    asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
+
+    FTRACE(2);
+    // ---- publish this CTA's strip tables, grid barrier ----
+    uint32_t* part = reinterpret_cast<uint32_t*>(ws + kWsHeaderFloats) + cols +
+                     (size_t)c * geo.max_strips * kD0SlotFloats;
+    for (int i = tid; i < nls * kD0SlotFloats; i += kFConsumers)
+        part[i] = skey[i >> 6][(i >> 5) & 1][i & 31];
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(ws) + kWsArriveIdx;
+    unsigned int* done = reinterpret_cast<unsigned int*>(ws) + kWsDoneIdx;
+    if (tid == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(arrive) : "memory");
+        unsigned int seen = 0, spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+            if (seen >= (unsigned int)G) break;
+            if (++spins > (1u << 26)) __trap();
+        }
+        __threadfence();
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
+
+    FTRACE(3);
+    // ---- parameters of every column of every strip this CTA touches ----
+    for (int i = tid; i < nls * 32; i += kFConsumers) {
+        const int ls = i >> 5, col = i & 31;
+        const int strip = s_first + ls;
+        const int ta = strip * tps, tb = ta + tps - 1;
+        const int c_lo = d0_cta_of_tile(ta, sp), c_hi = d0_cta_of_tile(tb, sp);
+        uint32_t kmn = 0xFFFFFFFFu, kmx = 0u;
+        for (int cc = c_lo; cc <= c_hi; ++cc) {
+            const int ls2 = strip - d0_first_tile(cc, sp) / tps;
+            const uint32_t* pp = reinterpret_cast<const uint32_t*>(ws + kWsHeaderFloats) + cols +
+                                 ((size_t)cc * geo.max_strips + ls2) * kD0SlotFloats;
+            kmn = min(kmn, __ldcg(pp + col));
+            kmx = max(kmx, __ldcg(pp + 32 + col));
+        }
+        const AffineParams ap = affine_params(float_of_key(kmn), float_of_key(kmx), L);
+        sparam[ls][0][col] = ap.mn; sparam[ls][1][col] = ap.scale; sparam[ls][2][col] = ap.rcp;
+        if (c == c_lo) { scale_out[(int64_t)strip * 32 + col] = ap.scale; zp_out[(int64_t)strip * 32 + col] = ap.mn; }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
+    if (tid == 0) {
+        const unsigned int old = atomicAdd(done, 1u);
+        if (old == (unsigned int)(G - 1)) { *arrive = 0u; *done = 0u; }
+    }
+
+    // ---- phase 2: codes.  Same (column quad, row phase) mapping with the 4 columns' parameters in
+    // registers; the 4 codes of a step go to a [128 rows x 32 B] staging tile of the group, which is
+    // then written out row per thread: one full 32-byte sector per store. ----
+    constexpr int kStageRow = (BITS == 4 && PACK) ? 16 : 32;
+    const uint32_t stage = smem + (uint32_t)nslots * kTileBytes + (uint32_t)group * (kFRows * 32);
+    float pa[4], ps[4], pr[4];
+    int par_ls = -1;
+    bool slow = false;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = a4, r4 = a4;
+    auto quantize_tile = [&](uint32_t tile_addr, int t) {
+        const int strip = t / tps;
+        if (strip - s_first != par_ls) {
+            par_ls = strip - s_first;
+            a4 = *reinterpret_cast<const float4*>(&sparam[par_ls][0][4 * cq]);
+            s4 = *reinterpret_cast<const float4*>(&sparam[par_ls][1][4 * cq]);
+            r4 = *reinterpret_cast<const float4*>(&sparam[par_ls][2][4 * cq]);
+            pa[0] = a4.x; pa[1] = a4.y; pa[2] = a4.z; pa[3] = a4.w;
+            ps[0] = s4.x; ps[1] = s4.y; ps[2] = s4.z; ps[3] = s4.w;
+            pr[0] = r4.x; pr[1] = r4.y; pr[2] = r4.z; pr[3] = r4.w;
+            slow = __any_sync(0xffffffffu, pr[0] == 0.0f || pr[1] == 0.0f || pr[2] == 0.0f || pr[3] == 0.0f);
+        }
+        if (slow) { d0_tile_slow<T, BITS, PACK>(tile_addr, stage, 32 * gw + rp, cq, a4, s4, r4); return; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 32 * gw + 4 * i + rp;
+            float f[4];
+            load4(tile_addr, row, f);
+            uint32_t u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = __fsub_rn(f[j], pa[j]);
+                const float q0 = __fmul_rn(a, pr[j]);
+                const float rem = __fmaf_rn(-ps[j], q0, a);
+                u[j] = __float_as_uint(__fadd_rn(__fmaf_rn(pr[j], rem, q0), kMagic));   // in [0, L]: no clamp needed
+            }
+            d0_stage4<BITS, PACK>(stage, row, cq, u);
+        }
+    };
+    // staging -> global: thread r owns row r of the tile
+    auto write_tile = [&](int t) {
+        const int strip = t / tps, rb = t - strip * tps;
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + group), "n"(kFRows) : "memory");      // staging complete
+        const int64_t grow = (int64_t)rb * kFRows + r;
+#ifdef QUANTA_D0_NOSTORE
+        if (grow < 0) {
+#else
+        if (grow < rows) {
+#endif
+            const int64_t e0 = grow * cols + (int64_t)strip * kRowElems;
+            if (kStageRow == 16) {
+                const uint4 o = lds128(stage + (uint32_t)r * 16u);
+                __stcs(reinterpret_cast<uint4*>(q_out + (e0 >> 1)), o);
+            } else {
+                const uint4 o0 = lds128(stage + (uint32_t)r * 32u), o1 = lds128(stage + (uint32_t)r * 32u + 16u);
+                asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"l"(q_out + e0), "r"(o0.x), "r"(o0.y), "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
+                             : "memory");
+            }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + group), "n"(kFRows) : "memory");      // staging may be overwritten
+    };
+    FTRACE(4);
+    FTRACE(5);
+    // resident tiles (shared memory) and re-streamed tiles (L2, newest first) alternate, so the ring's L2
+    // latency hides behind the resident tiles' arithmetic
+    const int m_end = 2 * ns;
+    int i2 = group;
+    int m2 = ns + ((group - (R + ns) % kFGroups + kFGroups) % kFGroups);
+    bool turn = false;
+#ifdef QUANTA_FUSED_TRACE
+    long long tw = 0, tq = 0, ts = 0, tc;
+#define FACC(acc) do { long long now = clock64(); acc += now - tc; tc = now; } while (0)
+    tc = clock64();
+#else
+#define FACC(acc) do { } while (0)
+#endif
+    while (i2 < R || m2 < m_end) {
+        const bool streamed = (m2 < m_end) && (turn || i2 >= R);
+        turn = !turn;
+        uint32_t ta; int t, slot = -1;
+        if (!streamed) {
+            ta = smem + i2 * kTileBytes; t = t0 + i2; i2 += kFGroups;
+        } else {
+            const int u = m2 / ring;
+            slot = R + (m2 - u * ring);
+            mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
+            ta = smem + slot * kTileBytes; t = t1 - 1 - (m2 - ns); m2 += kFGroups;
+        }
+        FACC(tw);
+        quantize_tile(ta, t);
+        if (slot >= 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);          // every lane has read its 8 chunks
+        }
+        FACC(tq);
+        write_tile(t);
+        FACC(ts);
+    }
+#ifdef QUANTA_FUSED_TRACE
+    if (tid == 0 && c == 0) printf("dim0 phase2: wait %lld quantize %lld write %lld slow %d\n", tw, tq, ts, (int)slow);
+#endif
+#ifdef QUANTA_FUSED_TRACE
+    FTRACE(6);
+    if (tid == 0 && (c == 0 || c == G - 1))
+        printf("dim0 cta %d cnt %d R %d ns %d nls %d: init %lld ph1 %lld barrier %lld params %lld regtile %lld rest %lld | total %lld\n",
+               c, cnt, R, ns, nls, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[6] - tr[0]);
+#endif
+}
+
+// --------------------------------------------------------------------------
 // 2b. the same stream over SEVERAL tensors in one launch (blockwise, convention A)
 // --------------------------------------------------------------------------
 // Quantizing a model is hundreds of independent matrices; one launch per matrix pays a
@@ -1263,6 +1615,58 @@ static int launch_tensor_fused(const T* x, int64_t n, int64_t n_rows, uint8_t* q
 static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// DIM0, convention A: one cooperative launch when the matrix tiles cleanly; returns -1 when the
+// shape is not eligible (the caller falls back to the multi-launch path).
+template <typename T, int BITS, bool PACK>
+static int launch_dim0_fused(const T* x, int64_t rows, int64_t cols, uint8_t* q, float* scale, float* zp, float* ws,
+                             cudaStream_t st) {
+    using RL = RowLayout<T>;
+    constexpr int kTileBytes = kFRows * RL::kRowBytes;
+    if (cols % kRowElems != 0 || !aligned16(x) || !aligned16(q) || !use_fused_tensor()) return -1;
+    // the second pass lives on L2 hits: beyond ~100 MB the re-read comes from HBM anyway and the
+    // multi-launch path (more CTAs in flight) measured faster
+    if ((double)rows * (double)cols * sizeof(T) > 100e6) return -1;
+    Dim0Geom geo;
+    const int64_t tps = (rows + kFRows - 1) / kFRows, n_strips = cols / kRowElems;
+    if (tps * n_strips > (int64_t)1 << 30) return -1;
+    geo.tps = (int)tps;
+    geo.n_tiles = (int)(tps * n_strips);
+    const int G = geo.n_tiles < kNumSMs ? geo.n_tiles : kNumSMs;
+    const int per_cta = (geo.n_tiles + G - 1) / G;
+    geo.max_strips = (per_cta + geo.tps - 1) / geo.tps + 1;
+    if (geo.max_strips > kD0MaxStrips) return -1;
+    CUtensorMap tmap;
+    int rc = make_tensor_map_2d(&tmap, TmaType<T>::v, sizeof(T), x, (uint64_t)cols, (uint64_t)rows,
+                                (uint64_t)cols * sizeof(T), kRowElems, kFRows,
+                                sizeof(T) == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    auto kern = quantize_dim0_fused_kernel<T, BITS, PACK>;
+    int nslots = (192 * 1024) / kTileBytes;                      // 12 x 16 KB; staging (16 KB) and the parameter tables (10 KB) take the rest
+    if (nslots > kFMaxSlots) nslots = kFMaxSlots;
+    int ring_min = (64 * 1024) / kTileBytes;
+    ring_min = (ring_min + kFGroups - 1) / kFGroups * kFGroups;
+    const int smem = nslots * kTileBytes + kFGroups * kFRows * 32 + 1024;      // + one staging tile per group
+    static bool attr_set = false;      // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)G);
+    cfg.blockDim = dim3(kFThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (const char* e = getenv("QUANTA_B200_FUSED_COOP")) { if (atoi(e) == 0) cfg.numAttrs = 0; }
+    return cuda_status(cudaLaunchKernelEx(&cfg, kern, tmap, rows, cols, geo, nslots, ring_min, q, scale, zp, ws));
+}
+
+
 // TENSOR / DIM0 body shared by conventions A and B.
 template <typename T, int BITS, bool PACK, int CONV>
 static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, uint8_t* q, float* scale, float* zp,
@@ -1303,6 +1707,10 @@ static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, ui
         return cuda_status(cudaGetLastError());
     }
     // DIM0
+    if (CONV == kConvA) {
+        const int rc = launch_dim0_fused<T, BITS, PACK>(x, rows, cols, q, scale, zp, ws, st);
+        if (rc >= 0) return rc;
+    }
     float* rcp = ws + kWsHeaderFloats;
     float* pmin = rcp + cols;
     int nchunks = (int)((rows + 63) / 64);
@@ -1432,7 +1840,9 @@ static int quantize_block_batch_t(const void* const* xs, const int64_t* numels, 
 
 size_t quantize_workspace_bytes(int64_t cols) {
     size_t tensor_part = (size_t)(kWsHeaderFloats + 64 + 2 * kMaxPartialCtas) * 4;
-    size_t dim0_part = (size_t)(kWsHeaderFloats + (int64_t)(2 * kMaxDim0Chunks + 1) * (cols < 1 ? 1 : cols)) * 4;
+    // multi-launch path: rcp + chunk partials; single-launch path: cols + (cols/32 + 3 * #SMs) partial slots of 64
+    size_t dim0_part = (size_t)(kWsHeaderFloats + (int64_t)(2 * kMaxDim0Chunks + 1) * (cols < 1 ? 1 : cols) +
+                                4 * kNumSMs * kD0SlotFloats + 64) * 4;
     return (tensor_part > dim0_part ? tensor_part : dim0_part) + 256;
 }
 

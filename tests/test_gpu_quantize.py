@@ -104,6 +104,34 @@ def test_tensor_and_dim0_vs_oracle(Q, shape, bits):
         assert_f32_bits(host(d), OC.dequantize_affine(qo, so, zo, mode, x.shape[1]), "dequant")
 
 
+@pytest.mark.parametrize("shape", [(2000, 4096), (4100, 2048), (8192, 1024), (130, 8192), (513, 32)])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_large_tensor_and_dim0_single_launch(Q, shape, bits):
+    """Sizes at which the single-launch kernels keep some tiles in shared memory / registers and
+    re-stream the rest (more tiles per CTA than slots), ragged last row tile, constant columns."""
+    rng = np.random.default_rng(shape[0] * 7 + bits)
+    x = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    x[:, 5] = 0.25                                      # constant column -> +1e-6 rule
+    x[:, 17] = 0.0
+    x[3, 30] = 40.0                                     # wide-range column
+    for mode in (0, 1):
+        q, s, z = quantize(Q, dev(x), bits, mode)
+        qo, so, zo = OC.quantize_affine(x, bits, mode)
+        assert_u8_equal(host(q), qo, f"codes mode={mode}")
+        assert_f32_bits(host(s), so, "scale")
+        assert_f32_bits(host(z), zo, "zp")
+    if bits == 4:
+        pk, s2, z2 = Q.quantize_4bit(dev(x), per_channel=True, packed=True)
+        qo, so, zo = OC.quantize_affine(x, 4, 1)
+        assert_u8_equal(host(pk), O.pack4(qo.reshape(-1)), "dim0 fused pack == pack(unpacked)")
+    xb = torch.from_numpy(x).to(torch.bfloat16)
+    for mode in (0, 1):
+        q, s, z = quantize(Q, xb.cuda(), bits, mode)
+        qo, so, zo = OC.quantize_affine(xb.float().numpy(), bits, mode)
+        assert_u8_equal(host(q), qo, f"bf16 codes mode={mode}")
+        assert_f32_bits(host(s), so, "bf16 scale")
+
+
 @pytest.mark.parametrize("block", [32, 64, 128, 256, 512, 1024, 2048, 16, 96, 6])
 @pytest.mark.parametrize("bits", [8, 4])
 def test_blockwise_vs_oracle(Q, block, bits):

@@ -10,3 +10,5 @@ for rows in (512, 4096, 11008):
         print("rows", rows, flush=True)
         Q.quantize_8bit(x)
         torch.cuda.synchronize()
+        Q.quantize_8bit(x, per_channel=True)
+        torch.cuda.synchronize()
