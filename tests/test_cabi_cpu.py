@@ -85,8 +85,9 @@ def test_error_behaviour_mirrors_reference():
 
 
 def test_workspace_sizes_are_small():
-    """Per-tensor mode needs a few KB; dim-0 mode scales with the column count only."""
+    """Per-tensor mode needs a fixed ~150 KB (partials of one CTA per SM for the single-launch kernels);
+    dim-0 mode scales with the column count only."""
     h = _lib.lib()
-    assert h.quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, 1, 1) < (1 << 16)
+    assert h.quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, 1, 1) < (1 << 18)
     assert h.quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, 11008, 4096) < (4 << 20)
     assert h.quanta_workspace_bytes(_lib.OP_BACKEND_DEQUANTIZE, 4096, 4096) == 256
