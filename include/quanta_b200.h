@@ -159,6 +159,26 @@ QUANTA_API int quanta_backend_dequantize(const uint8_t* q, int64_t rows, int64_t
                               const float* scale, const float* zp, float* out,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the rest of the quant_type switch (row N4): nf8, fp4, fp8 ---------------
+ *
+ * quantize_8bit(..., quant_type="nf8")  Quanta/functional/quantization.py:170-183:
+ *   256 levels tanh(2*linspace(-1,1,256)) (quanta_nf8_levels returns the reference's
+ *   own float32 values), abs-max normalisation, nearest level (first index on ties);
+ *   block = 0: whole tensor (the reference), block = 16 * 2^j <= 512: per block.
+ * quantize_4bit(..., "fp4") / quantize_8bit(..., "fp8")  :120-168:
+ *   code = sign | exponent field | mantissa, field = clamp(round(log2|x| + bias), 0, E)
+ *   with bias 1 / 7, E = 3 / 15 and 1 / 3 mantissa bits; one code per byte; zero
+ *   encodes as field = bias, mantissa 0 and decodes to 1.0 like the reference.
+ * dequantize_*bit(..., quant_type=...)  :39-49, :62-69.                          */
+QUANTA_API int quanta_nf8_levels(float* out256);
+QUANTA_API int quanta_quantize_nf8(const void* x, int x_dtype, int64_t n, int64_t block,
+                        uint8_t* q_out, float* absmax_out, void* stream);
+QUANTA_API int quanta_dequantize_nf8(const uint8_t* q, int64_t n, int64_t block, const float* absmax,
+                          void* out, int out_dtype, void* stream);
+QUANTA_API int quanta_quantize_fp(const void* x, int x_dtype, int64_t n, int bits, uint8_t* q_out, void* stream);
+QUANTA_API int quanta_dequantize_fp(const uint8_t* q, int64_t n, int bits, int bias,
+                         void* out, int out_dtype, void* stream);
+
 /* ---- dequantize-then-matmul behind Quanta/nn/linear.py -------------------
  *
  * Replaces the placeholder F.linear in Linear4bit.forward (nn/linear.py:81-83)

@@ -366,3 +366,90 @@ def dequantize_nf4(idx, absmax, block=None):
     if block is None:
         return (lv * F32(absmax)).astype(np.float32)
     return (lv.reshape(-1, block) * _f32(absmax).reshape(-1, 1)).astype(np.float32).reshape(idx.shape)
+
+
+# --------------------------------------------------------------------------
+# Row N4: nf8 / fp4 / fp8 (Quanta/functional/quantization.py:120-183, :39-49, :62-69)
+# --------------------------------------------------------------------------
+# The decisions that depend on torch's own libm (tanh for the nf8 levels, log2 for the fp exponent
+# field — neither is correctly rounded) are taken from tables derived by running the unmodified
+# reference (tests/golden/make_tables_n4.py): the level values, and for each exponent field the
+# smallest |x| that reaches it.  Everything else is restated arithmetic.
+
+def _n4_tables():
+    import os
+    global _N4
+    try:
+        return _N4
+    except NameError:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                            "quanta_tables_n4.npz")
+        _N4 = dict(np.load(path))
+        return _N4
+
+
+def nf8_levels():
+    return _n4_tables()["nf8_levels"].astype(np.float32)
+
+
+def quantize_nf8(x, block=None):
+    """``quantize_8bit_nf8`` (:170-183): as NF4 with the 256 tanh levels — the full distance matrix and
+    ``argmin`` (first index on ties), NOT the thresholds the CUDA kernel uses."""
+    lv = nf8_levels()
+    with np.errstate(all="ignore"):
+        x = _f32(x)
+        flat = x.reshape(-1) if block is None else x.reshape(-1, block)
+        ax = np.abs(flat)
+        am = np.max(ax, axis=-1, keepdims=True).astype(np.float32)
+        am = np.where(np.any(np.isnan(ax), axis=-1, keepdims=True), F32(np.nan), am).astype(np.float32)
+        normalized = (flat / am).astype(np.float32).reshape(-1)
+        idx = np.empty(normalized.shape, np.uint8)
+        for i in range(0, normalized.size, 1 << 16):              # bounded N x 256 temporaries
+            nb = normalized[i:i + (1 << 16)]
+            idx[i:i + nb.size] = np.argmin(np.abs((nb[:, None] - lv).astype(np.float32)), axis=-1)
+        return idx.reshape(x.shape), (am.reshape(()) if block is None else am.reshape(-1))
+
+
+def dequantize_nf8(idx, absmax, block=None):
+    """``dequantize_8bit(..., quant_type="nf8")`` (:39-41): levels[q] * abs_max."""
+    idx = np.asarray(idx)
+    lv = nf8_levels()[idx.astype(np.int64)]
+    if block is None:
+        return (lv * F32(absmax)).astype(np.float32)
+    return (lv.reshape(-1, block) * _f32(absmax).reshape(-1, 1)).astype(np.float32).reshape(idx.shape)
+
+
+def quantize_fp(x, bits):
+    """``quantize_4bit_fp4`` (:120-144) / ``quantize_8bit_fp8`` (:146-168): sign | exponent field |
+    mantissa.  field = clamp(round(log2(|x| + (|x| == 0)) + bias), 0, E) via the derived thresholds;
+    mantissa = clamp(round(|x| / 2^(field - bias) * M - M), 0, M - 1) in float32 (M = 2 / 8: the fp4
+    form ``round(v - 1)`` is the same expression with M = 1 ... clamp(0, 1))."""
+    t = _n4_tables()
+    bias, emax, thr = (1, 3, t["fp4_exp_thresholds"]) if bits == 4 else (7, 15, t["fp8_exp_thresholds"])
+    with np.errstate(all="ignore"):
+        x = _f32(x)
+        a = np.abs(x)
+        a0 = np.where(a == 0, F32(1.0), a).astype(np.float32)
+        field = np.searchsorted(thr.astype(np.float32), a0, side="right").astype(np.int64)      # #{k : a0 >= thr[k]}
+        field = np.minimum(field, emax)
+        scaled = (a / np.exp2((field - bias).astype(np.float32))).astype(np.float32)
+        if bits == 4:
+            m = np.clip(np.rint((scaled - F32(1.0)).astype(np.float32)), 0, 1)
+            code = (field << 1) | m.astype(np.int64)
+            code = np.where(x < 0, code | 0x8, code)
+        else:
+            m = np.clip(np.rint(((scaled * F32(8.0)).astype(np.float32) - F32(8.0)).astype(np.float32)), 0, 7)
+            code = (field << 3) | m.astype(np.int64)
+            code = np.where(x < 0, code | 0x80, code)
+        return code.astype(np.uint8)
+
+
+def dequantize_fp(q, bits, bias):
+    """fp4 (:62-69): (1 + m) * 2^(e - bias) * sign;  fp8 (:42-49): (1 + m / 8) * 2^(e - bias) * sign."""
+    q = np.asarray(q).astype(np.int64)
+    if bits == 4:
+        sign, e, frac = q & 0x8, (q >> 1) & 0x3, (q & 1).astype(np.float32)
+    else:
+        sign, e, frac = q & 0x80, (q >> 3) & 0xF, ((q & 7).astype(np.float32) / F32(8.0)).astype(np.float32)
+    val = ((F32(1.0) + frac).astype(np.float32) * np.exp2((e - int(bias)).astype(np.float32))).astype(np.float32)
+    return np.where(sign != 0, -val, val).astype(np.float32)

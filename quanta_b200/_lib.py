@@ -34,6 +34,11 @@ SIGNATURES = {
     "quanta_unpack4": (_int, [_vp, _i64, _vp, _vp]),
     "quanta_backend_quantize": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_backend_dequantize": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "quanta_nf8_levels": (_int, [_vp]),
+    "quanta_quantize_nf8": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp]),
+    "quanta_dequantize_nf8": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp]),
+    "quanta_quantize_fp": (_int, [_vp, _int, _i64, _int, _vp, _vp]),
+    "quanta_dequantize_fp": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp]),
     "quanta_gemm_wna16": (_int, [_vp, _int, _vp, _int, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "quanta_gemm_wna16_scatter": (_int, [_vp, _int, _vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _vp,
                                          _sz, _vp]),

@@ -22,7 +22,7 @@ import torch
 
 from .. import _host, _lib
 
-_NOT_BUILT = ("nf4", "fp4", "nf8", "fp8")      # nf4 is built; the others are 'next' rows (N4)
+_nf8_levels = {}
 _nf4_levels = {}
 
 
@@ -136,6 +136,94 @@ def _dequantize_nf4(q_tensor, absmax, blocksize, packed, shape, out_dtype):
     return out
 
 
+def nf8_levels(device):
+    """The 256 nf8 levels ``tanh(2 * linspace(-1, 1, 256))`` exactly as the reference's torch computes them
+    (second return value of ``quantize_8bit(..., quant_type="nf8")``, Quanta/functional/quantization.py:174-175)."""
+    import ctypes as C
+    key = str(device)
+    if key not in _nf8_levels:
+        buf = (C.c_float * 256)()
+        _lib.check(_lib.lib().quanta_nf8_levels(buf), "quanta_nf8_levels")
+        _nf8_levels[key] = torch.tensor(list(buf), dtype=torch.float32, device=device)
+    return _nf8_levels[key]
+
+
+def _prep_input(tensor):
+    _host.require_cuda(tensor)
+    x = tensor.detach()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return x, _host.dtype_code(x), x.numel(), x.device
+
+
+def _quantize_nf8(tensor, blocksize):
+    x, code, n, dev = _prep_input(tensor)
+    if n == 0:
+        raise RuntimeError("max(): cannot quantize an empty tensor")
+    B = 0 if blocksize is None else int(blocksize)
+    if B and n % B:
+        raise ValueError(f"numel ({n}) must be a multiple of blocksize ({blocksize})")
+    with torch.cuda.device(dev):
+        q = torch.empty(n, dtype=torch.uint8, device=dev)
+        absmax = torch.empty(n // B if B else 1, dtype=torch.float32, device=dev)
+        st = _lib.lib().quanta_quantize_nf8(x.data_ptr(), code, n, B, q.data_ptr(), absmax.data_ptr(), _host.stream_ptr(dev))
+    _lib.check(st, "quanta_quantize_nf8")
+    return q.reshape(tensor.shape), nf8_levels(dev), (absmax if B else absmax.reshape(()))
+
+
+def _dequantize_nf8(q_tensor, absmax, blocksize, out_dtype):
+    _host.require_cuda(q_tensor, "q_tensor")
+    dev = q_tensor.device
+    q = q_tensor.detach()
+    if q.dtype != torch.uint8:
+        q = q.to(torch.uint8)
+    if not q.is_contiguous():
+        q = q.contiguous()
+    absmax = torch.as_tensor(absmax, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+    n = q.numel()
+    out = torch.empty(q.shape, dtype=out_dtype, device=dev)
+    if n == 0:
+        return out
+    B = 0 if blocksize is None else int(blocksize)
+    if (B and absmax.numel() != n // B) or (not B and absmax.numel() != 1):
+        raise ValueError("absmax does not match blocksize")
+    with torch.cuda.device(dev):
+        st = _lib.lib().quanta_dequantize_nf8(q.data_ptr(), n, B, absmax.data_ptr(), out.data_ptr(),
+                                              _host._DTYPE[out_dtype], _host.stream_ptr(dev))
+    _lib.check(st, "quanta_dequantize_nf8")
+    return out
+
+
+def _quantize_fp(tensor, bits):
+    """fp4 / fp8: returns ``(codes, None, exp_bias)`` like the reference (:144, :168)."""
+    x, code, n, dev = _prep_input(tensor)
+    q = torch.empty(tensor.shape, dtype=torch.uint8, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            st = _lib.lib().quanta_quantize_fp(x.data_ptr(), code, n, bits, q.data_ptr(), _host.stream_ptr(dev))
+        _lib.check(st, "quanta_quantize_fp")
+    return q, None, (1 if bits == 4 else 7)
+
+
+def _dequantize_fp(q_tensor, bias, bits, out_dtype):
+    _host.require_cuda(q_tensor, "q_tensor")
+    dev = q_tensor.device
+    q = q_tensor.detach()
+    if q.dtype != torch.uint8:
+        q = q.to(torch.uint8)
+    if not q.is_contiguous():
+        q = q.contiguous()
+    if float(bias) != int(bias):
+        raise ValueError("the exponent bias must be an integer")
+    out = torch.empty(q.shape, dtype=out_dtype, device=dev)
+    if q.numel():
+        with torch.cuda.device(dev):
+            st = _lib.lib().quanta_dequantize_fp(q.data_ptr(), q.numel(), bits, int(bias), out.data_ptr(),
+                                                 _host._DTYPE[out_dtype], _host.stream_ptr(dev))
+        _lib.check(st, "quanta_dequantize_fp")
+    return out
+
+
 def quantize_4bit(tensor, quant_type="linear", per_channel=False, blocksize=None, packed=False):
     """Quantize a floating-point tensor to 4-bit precision (codes 0..15, one per
     uint8 unless ``packed``).  Mirrors Quanta/functional/quantization.py:7-18."""
@@ -144,8 +232,8 @@ def quantize_4bit(tensor, quant_type="linear", per_channel=False, blocksize=None
     if quant_type == "nf4":
         # returns (indices, nf4_levels, abs_max) like the reference (:118)
         return _quantize_nf4(tensor, blocksize, packed)
-    if quant_type in _NOT_BUILT[1:2]:
-        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N1/N4), not built yet")
+    if quant_type == "fp4":
+        return _quantize_fp(tensor, 4)
     raise ValueError(f"Unknown quantization type: {quant_type}")
 
 
@@ -154,8 +242,11 @@ def quantize_8bit(tensor, quant_type="linear", per_channel=False, blocksize=None
     Mirrors Quanta/functional/quantization.py:20-31."""
     if quant_type == "linear":
         return _quantize_linear(tensor, 8, per_channel, blocksize, False)
-    if quant_type in _NOT_BUILT[2:]:
-        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N4), not built yet")
+    if quant_type == "nf8":
+        # returns (indices, nf8_levels, abs_max) like the reference (:183)
+        return _quantize_nf8(tensor, blocksize)
+    if quant_type == "fp8":
+        return _quantize_fp(tensor, 8)
     raise ValueError(f"Unknown quantization type: {quant_type}")
 
 
@@ -263,8 +354,11 @@ def dequantize_8bit(q_tensor, scale_or_levels, zero_point_or_bias, quant_type="l
     ``q.float() * scale + zero_point`` (Quanta/functional/quantization.py:33-38)."""
     if quant_type == "linear":
         return _dequantize_linear(q_tensor, scale_or_levels, zero_point_or_bias, blocksize, False, None, out_dtype)
-    if quant_type in _NOT_BUILT[2:]:
-        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N4), not built yet")
+    if quant_type == "nf8":
+        # scale_or_levels is the nf8_levels tensor, zero_point_or_bias the abs_max (:39-41)
+        return _dequantize_nf8(q_tensor, zero_point_or_bias, blocksize, out_dtype)
+    if quant_type == "fp8":
+        return _dequantize_fp(q_tensor, zero_point_or_bias, 8, out_dtype)
     raise ValueError(f"Unknown quantization type: {quant_type}")
 
 
@@ -278,6 +372,6 @@ def dequantize_4bit(q_tensor, scale_or_levels, zero_point_or_bias, quant_type="l
     if quant_type == "nf4":
         # scale_or_levels is the nf4_levels tensor, zero_point_or_bias the abs_max (:59-61)
         return _dequantize_nf4(q_tensor, zero_point_or_bias, blocksize, packed, shape, out_dtype)
-    if quant_type in _NOT_BUILT[1:2]:
-        raise NotImplementedError(f"quant_type={quant_type!r} is a 'next' row (SURVEY §8(f) N1/N4), not built yet")
+    if quant_type == "fp4":
+        return _dequantize_fp(q_tensor, zero_point_or_bias, 4, out_dtype)
     raise ValueError(f"Unknown quantization type: {quant_type}")

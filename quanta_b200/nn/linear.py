@@ -161,8 +161,8 @@ class Linear4bit(_QuantLinearBase):
 
     def _check_quant_type(self):
         if self.quant_type not in ("linear", "nf4"):
-            raise NotImplementedError(f"quant_type={self.quant_type!r} is a 'next' row (SURVEY §8(f) N4); "
-                                      "'nf4' and 'linear' are built")
+            raise NotImplementedError(f"quant_type={self.quant_type!r}: only 'nf4' and 'linear' have a fused dequant-GEMM; "
+                                      "fp4 is available as quantize_4bit / dequantize_4bit (SURVEY §8(f) N4)")
 
     @torch.no_grad()
     def quantize_(self):

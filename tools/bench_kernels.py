@@ -139,6 +139,21 @@ def mk_nf4(i):
 timeit("dequantize_4bit nf4 packed block64 -> fp32 (N1)", shape, n * (0.5 + 4 + 4 / 64), mk_nf4,
        lambda t: Q.dequantize_4bit(*t, quant_type="nf4", blocksize=64, packed=True, shape=shape), 3)
 
+# nf8 / fp4 / fp8 (row N4): one code byte per element
+timeit("quantize_8bit nf8 per-tensor (N4, two-pass)", shape, n * 5.0, lambda i: randn(shape, i),
+       lambda x: Q.quantize_8bit(x, quant_type="nf8"), 3)
+timeit("quantize_8bit nf8 block64 (N4)", shape, n * (4 + 1 + 4 / 64), lambda i: randn(shape, i),
+       lambda x: Q.quantize_8bit(x, quant_type="nf8", blocksize=64), 3)
+timeit("quantize_8bit fp8 (N4)", shape, n * 5.0, lambda i: randn(shape, i),
+       lambda x: Q.quantize_8bit(x, quant_type="fp8"), 3)
+timeit("quantize_4bit fp4 (N4, one code per byte)", shape, n * 5.0, lambda i: randn(shape, i),
+       lambda x: Q.quantize_4bit(x, quant_type="fp4"), 3)
+timeit("dequantize_8bit fp8 -> fp32 (N4)", shape, n * 5.0, lambda i: Q.quantize_8bit(randn(shape, i), quant_type="fp8")[0],
+       lambda q: Q.dequantize_8bit(q, None, 7, quant_type="fp8"), 3)
+timeit("dequantize_8bit nf8 block64 -> fp32 (N4)", shape, n * (1 + 4 + 4 / 64),
+       lambda i: Q.quantize_8bit(randn(shape, i), quant_type="nf8", blocksize=64),
+       lambda t: Q.dequantize_8bit(*t, quant_type="nf8", blocksize=64), 3)
+
 # batched blockwise quantize (one decoder layer's 7 matrices per call)
 layer = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
 nl = sum(a * b for a, b in layer)
