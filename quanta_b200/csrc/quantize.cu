@@ -1565,6 +1565,20 @@ static int launch_rows_tma(const T* x, int64_t n_rows, int lanes_per_block, uint
     return launch_rows_tma_impl<T, BITS, PACK, CONV, BLOCKWISE, false>(tmap, n_rows, lanes_per_block, q, scale, zp, ws, nparts, st);
 }
 
+// SMs of the current device (the single-launch kernels put one CTA on each and synchronise them with
+// a grid barrier, so the grid must never exceed what is really there); cached per device.
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+        cached[dev] = n < kNumSMs ? n : kNumSMs;          // the workspace partial slots are sized for kNumSMs
+    }
+    return cached[dev];
+}
+
 static bool use_fused_tensor() {
     static const bool v = []() {
         const char* e = getenv("QUANTA_B200_TWO_PASS");          // escape hatch: separate reduce + quantize launches
@@ -1599,7 +1613,8 @@ static int launch_tensor_fused(const T* x, int64_t n, int64_t n_rows, uint8_t* q
     }
     const int64_t n_tiles = (n_rows + kFRows - 1) / kFRows;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs));
+    const int sms = sm_count();
+    cfg.gridDim = dim3((unsigned)(n_tiles < sms ? n_tiles : sms));
     cfg.blockDim = dim3(kFThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -1631,7 +1646,8 @@ static int launch_dim0_fused(const T* x, int64_t rows, int64_t cols, uint8_t* q,
     if (tps * n_strips > (int64_t)1 << 30) return -1;
     geo.tps = (int)tps;
     geo.n_tiles = (int)(tps * n_strips);
-    const int G = geo.n_tiles < kNumSMs ? geo.n_tiles : kNumSMs;
+    const int sms = sm_count();
+    const int G = geo.n_tiles < sms ? geo.n_tiles : sms;
     const int per_cta = (geo.n_tiles + G - 1) / G;
     geo.max_strips = (per_cta + geo.tps - 1) / geo.tps + 1;
     if (geo.max_strips > kD0MaxStrips) return -1;

@@ -50,3 +50,25 @@ def test_nf4_large_random_matches_oracle(shape, block, packed):
     assert same_bits(d.cpu().numpy(), O.dequantize_nf4(io, ao, block))
     # size-independent property: every value lands on one of the 16 levels times its abs_max, error <= half a gap
     assert float((d.cpu() - x).abs().max()) <= 0.16 * float(x.abs().max())
+
+
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_nf4_many_equals_one_call_per_tensor(packed, dtype):
+    """The batched launch (and the TMA-stream path behind blocksize=64) give the bits of the per-tensor calls,
+    which the tests above pin to the reference."""
+    import quanta_b200 as Q
+    g = torch.Generator().manual_seed(11)
+    shapes = [(256, 512), (300, 64), (1, 64), (1024, 1024), (77, 128), (4096, 320)]
+    xs = [(torch.randn(*sh, generator=g) * (0.02 + i)).to(dtype).cuda() for i, sh in enumerate(shapes)]
+    xs[2].zero_()                                     # an all-zero block: 0/0 -> code 0
+    many = Q.quantize_nf4_many(xs, blocksize=64, packed=packed)
+    for x, (q, lv, am) in zip(xs, many):
+        io, ao = O.quantize_nf4(x.float().cpu().numpy().reshape(-1), 64)
+        got = q.cpu().numpy().reshape(-1)
+        if packed:
+            got = O.unpack4(got)[: x.numel()]
+        assert np.array_equal(got, io)
+        assert same_bits(am.cpu().numpy(), ao)
+        q1, _, am1 = Q.quantize_4bit(x, quant_type="nf4", blocksize=64, packed=packed)
+        assert torch.equal(q1.reshape(-1), q.reshape(-1)) and torch.equal(am1, am)
