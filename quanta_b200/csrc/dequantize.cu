@@ -89,14 +89,42 @@ __global__ void __launch_bounds__(256) dequant_flat_kernel(const uint8_t* __rest
                                                            const int* __restrict__ flag, float off) {
     const bool sym = CONV == kDqB && flag[0] != 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+    // per-tensor parameters (block == 0) are fetched and prepared once
+    DqParam p0{0.0f, 0.0f, 0.0f};
+    if (block == 0) {
+        p0.s = __ldg(scale); p0.z = __ldg(zp);
+        if (CONV == kDqB) p0.rcp = dq_rcp(p0.s, p0.z);
+    }
+    auto emit = [&](int64_t g, uint32_t w, float ps, float pz) {
         const int64_t i = g * 4;
-        uint32_t w = load_codes4<PACKED>(q, i);
-        int64_t b = block == 0 ? 0 : (block_shift >= 0 ? (i >> block_shift) : (i / block));
-        DqParam p{__ldg(scale + b), __ldg(zp + b), 0.0f};
-        if (CONV == kDqB) p.rcp = dq_rcp(p.s, p.z);
+        DqParam p = p0;
+        if (block != 0) {
+            p.s = ps; p.z = pz;
+            if (CONV == kDqB) p.rcp = dq_rcp(p.s, p.z);
+        }
         store4<OUT>(out + i, dq_value<CONV>(byte_to_f32<0>(w), p, sym, off), dq_value<CONV>(byte_to_f32<1>(w), p, sym, off),
                     dq_value<CONV>(byte_to_f32<2>(w), p, sym, off), dq_value<CONV>(byte_to_f32<3>(w), p, sym, off));
+    };
+    auto pidx = [&](int64_t g) -> int64_t {
+        const int64_t i = g * 4;
+        return block == 0 ? 0 : (block_shift >= 0 ? (i >> block_shift) : (i / block));
+    };
+    // 4 codes per thread per step keep a warp's accesses contiguous; 4 steps are in flight per thread
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + 3 * stride < n4; g += 4 * stride) {
+        uint32_t w[4]; float ps[4], pz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w[k] = load_codes4<PACKED>(q, (g + k * stride) * 4);
+            ps[k] = pz[k] = 0.0f;
+            if (block != 0) { const int64_t b = pidx(g + k * stride); ps[k] = __ldg(scale + b); pz[k] = __ldg(zp + b); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit(g + k * stride, w[k], ps[k], pz[k]);
+    }
+    for (; g < n4; g += stride) {
+        const int64_t b = pidx(g);
+        emit(g, load_codes4<PACKED>(q, g * 4), block != 0 ? __ldg(scale + b) : 0.0f, block != 0 ? __ldg(zp + b) : 0.0f);
     }
 }
 
