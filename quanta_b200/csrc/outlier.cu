@@ -17,6 +17,8 @@
 //                               outlier columns on the CUDA cores and stores y
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace quanta {
 
 constexpr int kOTileN = 128;      // output features per CTA (UMMA M)
@@ -126,24 +128,34 @@ struct OutlierParams {
     int mb;           // UMMA N: batch rows per CTA (multiple of 16, <= 256)
     int stages;
     int tmem_cols;
+    int y_tma;        // y leaves through shared-memory staging + TMA stores (pointer / pitch aligned)
     uint32_t a_bytes, b_bytes;
 };
+constexpr int kOJ = 32;           // outlier columns handled per pass of the epilogue
+constexpr uint32_t kOEpiBytes = 2 * 16 * 128 * 2 + kOJ * 256 * 4 + kOJ * 128 * 4 + 256 * 4;
 
 template <typename ACT>
 __global__ void __launch_bounds__(kOThreads, 1)
 int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                 const ACT* __restrict__ x, const int8_t* __restrict__ qw, const float* __restrict__ cw,
+                 const __grid_constant__ CUtensorMap tmap_y, const ACT* __restrict__ x, const int8_t* __restrict__ qw, const float* __restrict__ cw,
                  const float* __restrict__ cx, const int* __restrict__ jlist, const int* __restrict__ jcount,
                  const ACT* __restrict__ bias, ACT* __restrict__ y, const __grid_constant__ OutlierParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[kOMaxStages], empty[kOMaxStages], d_full;
     __shared__ uint32_t tmem_slot;
+    // epilogue tables, carved from dynamic shared memory behind the operand ring (kOEpiBytes):
+    //   ystage[2][16][128] 16-bit (TMA-store staging) | xo[kOJ][256] | wos[kOJ][128] | cxs[256]
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int n0 = blockIdx.x * kOTileN, m0 = blockIdx.y * p.mb;
     const int nk = (p.K + kOBlockK - 1) / kOBlockK;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    uint8_t* epi = smem_raw + (smem - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes;       // 1 KB aligned
+    uint16_t (*ystage)[16][kOTileN] = reinterpret_cast<uint16_t (*)[16][kOTileN]>(epi);
+    float (*xo)[256] = reinterpret_cast<float (*)[256]>(epi + 2 * 16 * kOTileN * 2);             // x[m0 + m, J[t]]
+    float (*wos)[kOTileN] = reinterpret_cast<float (*)[kOTileN]>(epi + 2 * 16 * kOTileN * 2 + kOJ * 256 * 4);   // round_act(qw[n, J[t]] / cw[n])
+    float* cxs = reinterpret_cast<float*>(epi + 2 * 16 * kOTileN * 2 + kOJ * 256 * 4 + kOJ * kOTileN * 4);      // cx[m0 + m]
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -207,16 +219,33 @@ int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     } else {
         // ===== epilogue: TMEM lane = output feature =====
         const int quarter = warp & 3;
-        const int gn = n0 + 32 * quarter + lane;
+        const int row = 32 * quarter + lane;
+        const int etid = tid - 64;                                  // 0..127 over the 4 epilogue warps
+        const int gn = n0 + row;
         const bool n_ok = gn < p.N;
         const float cwn = n_ok ? cw[gn] : 1.0f;
         const float b = (bias != nullptr && n_ok) ? ld_act(bias + gn) : 0.0f;
         const int nj = *jcount;
         const int8_t* qrow = qw + (int64_t)(n_ok ? gn : 0) * p.K;
+        const int m_valid = min(p.mb, p.M - m0);
+        if (etid == 0 && p.y_tma) prefetch_tensormap(&tmap_y);
+        // while the main loop runs: this tile's row multipliers and the first pass of outlier operands
+        for (int m = etid; m < p.mb; m += 128) cxs[m] = m < m_valid ? cx[m0 + m] : 1.0f;
+        auto stage_outliers = [&](int t0) {
+            const int nt = min(kOJ, nj - t0);
+            for (int t = 0; t < nt; ++t) {
+                const int jc = jlist[t0 + t];
+                // x[m, j] * round_act(qw[n, j] / cw[n]): the weight factor of this thread's feature
+                wos[t][row] = round_act<ACT>(__fdiv_rn((float)qrow[jc], cwn));
+                for (int m = etid; m < p.mb; m += 128) xo[t][m] = m < m_valid ? ld_act(x + (int64_t)(m0 + m) * p.K + jc) : 0.0f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        const bool single_pass = nj <= kOJ;
+        if (single_pass) stage_outliers(0); else asm volatile("bar.sync 1, 128;" ::: "memory");      // cxs visible
         mbar_wait(&d_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16);
-        const int m_valid = min(p.mb, p.M - m0);
         for (int c0 = 0; c0 < p.mb; c0 += 16) {
             uint32_t r[16];
             asm volatile(
@@ -225,29 +254,57 @@ int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                 : "r"(taddr + c0) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c0 >= m_valid) continue;
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int m = m0 + c0 + j;
-                const float cxm = (c0 + j < m_valid) ? cx[m] : 1.0f;
                 // float(acc) / (cx * cw): true divide by the rounded product (oracle arithmetic)
-                v[j] = __fdiv_rn((float)(int)r[j], __fmul_rn(cxm, cwn));
+                v[j] = __fdiv_rn((float)(int)r[j], __fmul_rn(cxs[c0 + j], cwn));
             }
-            // outlier columns: x[m, j] * round_act(qw[n, j] / cw[n]), fp32 accumulate
-            for (int t = 0; t < nj; ++t) {
-                const int jc = jlist[t];
-                const float wo = round_act<ACT>(__fdiv_rn((float)qrow[jc], cwn));
+            // outlier columns in list order, fp32 fma chain (oracle order)
+            if (single_pass) {
+                for (int t = 0; t < nj; ++t) {
+                    const float wo = wos[t][row];
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < m_valid) v[j] = __fmaf_rn(ld_act(x + (int64_t)(m0 + c0 + j) * p.K + jc), wo, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = __fmaf_rn(xo[t][c0 + j], wo, v[j]);
+                }
+            } else {
+                // many outliers: passes of kOJ columns staged through shared memory (all 128 threads take part)
+                for (int t0 = 0; t0 < nj; t0 += kOJ) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");      // previous pass fully read
+                    stage_outliers(t0);
+                    const int nt = min(kOJ, nj - t0);
+                    for (int t = 0; t < nt; ++t) {
+                        const float wo = wos[t][row];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __fmaf_rn(xo[t][c0 + j], wo, v[j]);
+                    }
+                }
             }
-            if (n_ok) {
+            if (p.y_tma) {
+                // [16 rows x 128 features] in the activation type -> one TMA store per chunk (rows past M and
+                // features past N are clipped by the tensor map)
+                uint16_t (*sb)[kOTileN] = ystage[(c0 >> 4) & 1];
+                if (etid == 0 && c0 >= 32) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const ACT o = to_act<ACT>(v[j] + b);
+                    sb[j][row] = *reinterpret_cast<const uint16_t*>(&o);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (etid == 0 && c0 < m_valid) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmap_y)), "r"(smem_u32(&sb[0][0])), "r"(n0), "r"(m0 + c0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (n_ok) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (c0 + j < m_valid) y[(int64_t)(m0 + c0 + j) * p.N + gn] = to_act<ACT>(v[j] + b);
             }
         }
+        if (p.y_tma && etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -286,10 +343,24 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     int mb = (int)((M + 15) / 16 * 16);
     if (mb > 256) mb = 256;
+    // one tile per CTA: pick the batch tile (256 / 128 / 64) that minimises waves x per-tile cost, the cost
+    // of a tile being its batch rows plus a fixed part (weight tile, pipeline fill) worth ~64 rows
+    if (mb > 64) {
+        const int64_t n_tiles_n = (N + kOTileN - 1) / kOTileN;
+        int best = mb;
+        int64_t best_cost = -1;
+        for (int cand = mb; cand >= 64 && cand % 16 == 0; cand /= 2) {
+            const int64_t tiles = n_tiles_n * ((M + cand - 1) / cand);
+            const int64_t cost = ((tiles + kNumSMs - 1) / kNumSMs) * (cand + 64);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cand; }
+            if (cand % 32 != 0) break;
+        }
+        mb = best;
+    }
     p.mb = mb;
     p.a_bytes = kOTileN * kOBlockK;
     p.b_bytes = (uint32_t)mb * kOBlockK;
-    int stages = (int)((200u * 1024u) / (p.a_bytes + p.b_bytes));
+    int stages = (int)((150u * 1024u) / (p.a_bytes + p.b_bytes));      // the epilogue's tables take ~58 KB of static shared memory
     if (stages > kOMaxStages) stages = kOMaxStages;
     p.stages = stages;
     int cols = 32; while (cols < mb) cols <<= 1;
@@ -302,8 +373,16 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
     rc = make_tensor_map_2d(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, qx, (uint64_t)K, (uint64_t)M, (uint64_t)K, kOBlockK,
                             (uint32_t)mb, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    CUtensorMap tmap_y = tmap_w;                         // placeholder unless y can take TMA stores
+    p.y_tma = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (N & 7) == 0) ? 1 : 0;
+    if (p.y_tma) {
+        rc = make_tensor_map_2d(&tmap_y, sizeof(ACT) == 2 && std::is_same<ACT, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                                              : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                2, y, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, kOTileN, 16, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
     auto kern = int8_gemm_kernel<ACT>;
-    const int smem = (int)(p.stages * (p.a_bytes + p.b_bytes) + 1024);
+    const int smem = (int)(p.stages * (p.a_bytes + p.b_bytes) + kOEpiBytes + 1024);
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -311,7 +390,7 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
         smem_set = smem;
     }
     dim3 grid((unsigned)((N + kOTileN - 1) / kOTileN), (unsigned)((M + mb - 1) / mb));
-    kern<<<grid, kOThreads, smem, st>>>(tmap_w, tmap_x, x, qw, cw, cx, jlist, jcount, bias, y, p);
+    kern<<<grid, kOThreads, smem, st>>>(tmap_w, tmap_x, tmap_y, x, qw, cw, cx, jlist, jcount, bias, y, p);
     return cuda_status(cudaGetLastError());
 }
 
