@@ -17,6 +17,7 @@
 //                               outlier columns on the CUDA cores and stores y
 #include "common.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace quanta {
@@ -47,7 +48,8 @@ __global__ void __launch_bounds__(256) outlier_colmax_kernel(const ACT* __restri
     const int r0 = blockIdx.y * 64, r1 = min(M, r0 + 64);
     float mx = 0.0f;
     for (int i = r0; i < r1; ++i) mx = fmaxf(mx, fabsf(ld_act(x + (int64_t)i * K + c)));
-    atomicMax(colmax + c, __float_as_uint(mx));
+    if (gridDim.y == 1) colmax[c] = __float_as_uint(mx);        // one chunk covers every row: no merge, no memset needed
+    else atomicMax(colmax + c, __float_as_uint(mx));
 }
 
 // 1b. flags and the ordered list J: one CTA, block-wide exclusive scan per 1024 columns.
@@ -129,6 +131,7 @@ struct OutlierParams {
     int stages;
     int tmem_cols;
     int y_tma;        // y leaves through shared-memory staging + TMA stores (pointer / pitch aligned)
+    int splits;       // K is cut into `splits` ranges (gridDim.z); int32 partial sums meet in `acc` (exact, order-free)
     uint32_t a_bytes, b_bytes;
 };
 constexpr int kOJ = 32;           // outlier columns handled per pass of the epilogue
@@ -139,7 +142,8 @@ __global__ void __launch_bounds__(kOThreads, 1)
 int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const __grid_constant__ CUtensorMap tmap_y, const ACT* __restrict__ x, const int8_t* __restrict__ qw, const float* __restrict__ cw,
                  const float* __restrict__ cx, const int* __restrict__ jlist, const int* __restrict__ jcount,
-                 const ACT* __restrict__ bias, ACT* __restrict__ y, const __grid_constant__ OutlierParams p) {
+                 const ACT* __restrict__ bias, ACT* __restrict__ y, int* __restrict__ acc,
+                 unsigned int* __restrict__ tile_counters, const __grid_constant__ OutlierParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[kOMaxStages], empty[kOMaxStages], d_full;
     __shared__ uint32_t tmem_slot;
@@ -149,8 +153,12 @@ int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int n0 = blockIdx.x * kOTileN, m0 = blockIdx.y * p.mb;
-    const int nk = (p.K + kOBlockK - 1) / kOBlockK;
+    const int nk_all = (p.K + kOBlockK - 1) / kOBlockK;
+    // split-K: this CTA's range of 128-K blocks
+    const int kb_lo = (int)((int64_t)nk_all * blockIdx.z / p.splits), kb_hi = (int)((int64_t)nk_all * (blockIdx.z + 1) / p.splits);
+    const int nk = kb_hi - kb_lo;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    __shared__ int last_flag;
     uint8_t* epi = smem_raw + (smem - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes;       // 1 KB aligned
     uint16_t (*ystage)[16][kOTileN] = reinterpret_cast<uint16_t (*)[16][kOTileN]>(epi);
     float (*xo)[256] = reinterpret_cast<float (*)[256]>(epi + 2 * 16 * kOTileN * 2);             // x[m0 + m, J[t]]
@@ -181,8 +189,8 @@ int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             if (elect_one_o()) {
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
                 const uint32_t dst = smem + (uint32_t)s * stage_bytes;
-                tma_load_2d_o(dst, &tmap_w, smem_u32(&full[s]), kb * kOBlockK, n0);
-                tma_load_2d_o(dst + p.a_bytes, &tmap_x, smem_u32(&full[s]), kb * kOBlockK, m0);
+                tma_load_2d_o(dst, &tmap_w, smem_u32(&full[s]), (kb_lo + kb) * kOBlockK, n0);
+                tma_load_2d_o(dst + p.a_bytes, &tmap_x, smem_u32(&full[s]), (kb_lo + kb) * kOBlockK, m0);
             }
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -246,14 +254,51 @@ int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         mbar_wait(&d_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16);
+        bool from_acc = false;
+        if (p.splits > 1) {
+            // int32 partial sums are exact, so the K ranges may meet in any order: add this range into the
+            // (zero-initialised) accumulator, then the CTA that arrives last at the tile's counter finishes the tile
+            for (int c0 = 0; c0 < m_valid; c0 += 16) {
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + c0) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (n_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < m_valid) atomicAdd(acc + (int64_t)(m0 + c0 + j) * p.N + gn, (int)r[j]);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (etid == 0) {
+                __threadfence();
+                const unsigned int old = atomicAdd(tile_counters + blockIdx.y * gridDim.x + blockIdx.x, 1u);
+                __threadfence();
+                last_flag = (old == (unsigned int)(p.splits - 1)) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            from_acc = true;
+        }
+        if (from_acc && !last_flag) {
+            // not the last range of this tile: nothing more to do
+        } else
         for (int c0 = 0; c0 < p.mb; c0 += 16) {
             uint32_t r[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr + c0) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!from_acc) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + c0) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    r[j] = (n_ok && c0 + j < m_valid) ? (uint32_t)__ldcg(acc + (int64_t)(m0 + c0 + j) * p.N + gn) : 0u;
+            }
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -317,8 +362,12 @@ int8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 // workspace: [flags K][colmax K uints][jcount + jlist (K+1 ints)][cx M floats][qx M*K bytes]
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// split-K accumulator: only problems whose int32 result fits this region are split (small token counts)
+constexpr size_t kOAccBytes = 4u << 20, kOCounterBytes = 16u << 10;
+
 size_t int8_outlier_workspace_bytes(int64_t M, int64_t K) {
-    return align256((size_t)K) + align256((size_t)K * 4) + align256((size_t)(K + 1) * 4) + align256((size_t)M * 4) + align256((size_t)M * (size_t)K) + 512;
+    return align256((size_t)K) + align256((size_t)K * 4) + kOCounterBytes + kOAccBytes + align256((size_t)(K + 1) * 4) +
+           align256((size_t)M * 4) + align256((size_t)M * (size_t)K) + 512;
 }
 
 template <typename ACT>
@@ -327,26 +376,24 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
     if (ws_bytes < int8_outlier_workspace_bytes(M, K)) return QUANTA_EWORKSPACE;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     uint8_t* flag = ws;
+    // [colmax | tile counters | acc] are contiguous: one memset clears what this call needs of them
     unsigned int* colmax = reinterpret_cast<unsigned int*>(ws + align256((size_t)K));
-    int* jcount = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(colmax) + align256((size_t)K * 4));
+    unsigned int* counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(colmax) + align256((size_t)K * 4));
+    int* acc = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(counters) + kOCounterBytes);
+    int* jcount = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(acc) + kOAccBytes);
     int* jlist = jcount + 1;
     float* cx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(jcount) + align256((size_t)(K + 1) * 4));
     int8_t* qx = reinterpret_cast<int8_t*>(reinterpret_cast<uint8_t*>(cx) + align256((size_t)M * 4));
 
-    cudaError_t me = cudaMemsetAsync(colmax, 0, (size_t)K * 4, st);
-    if (me != cudaSuccess) return (int)me;
-    outlier_colmax_kernel<ACT><<<dim3((unsigned)((K + 255) / 256), (unsigned)((M + 63) / 64)), 256, 0, st>>>(x, (int)M, (int)K, colmax);
-    outlier_columns_kernel<<<1, 1024, 0, st>>>(colmax, (int)K, threshold, flag, jlist, jcount);
-    outlier_rowquant_kernel<ACT><<<(unsigned)M, 256, 0, st>>>(x, (int)K, flag, cx, qx);
-
+    // tiling first: the split-K decision sizes the memset
     OutlierParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     int mb = (int)((M + 15) / 16 * 16);
     if (mb > 256) mb = 256;
+    const int64_t n_tiles_n = (N + kOTileN - 1) / kOTileN;
     // one tile per CTA: pick the batch tile (256 / 128 / 64) that minimises waves x per-tile cost, the cost
     // of a tile being its batch rows plus a fixed part (weight tile, pipeline fill) worth ~64 rows
     if (mb > 64) {
-        const int64_t n_tiles_n = (N + kOTileN - 1) / kOTileN;
         int best = mb;
         int64_t best_cost = -1;
         for (int cand = mb; cand >= 64 && cand % 16 == 0; cand /= 2) {
@@ -358,6 +405,27 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
         mb = best;
     }
     p.mb = mb;
+    // split K while SMs would idle: small batches only (the int32 accumulator region is fixed-size)
+    const int64_t tiles = n_tiles_n * ((M + mb - 1) / mb);
+    const int nk_all = (int)((K + kOBlockK - 1) / kOBlockK);
+    int splits = 1;
+    // (measured: pays off for long K only — at K = 4096 the larger memset and the atomics cost more than the
+    // shorter main loop saves: 20.3 -> 23.2 us at one token on 4096 x 4096, but 51.7 -> 42.8 us at K = 16384)
+    if (nk_all >= 64 && (size_t)M * (size_t)N * 4 <= kOAccBytes && tiles * 4 <= (int64_t)kOCounterBytes) {
+        while (splits < 16 && tiles * (splits * 2) <= kNumSMs && nk_all / (splits * 2) >= 4) splits *= 2;
+    }
+    if (const char* e = getenv("QUANTA_B200_OUTLIER_SPLITS")) { int v = atoi(e); if (v == 1) splits = 1; }
+    p.splits = splits;
+    if (splits > 1 || M > 64) {
+        size_t clear = (size_t)K * 4;
+        if (splits > 1) clear = align256((size_t)K * 4) + kOCounterBytes + (size_t)M * (size_t)N * 4;
+        cudaError_t me = cudaMemsetAsync(colmax, 0, clear, st);
+        if (me != cudaSuccess) return (int)me;
+    }
+    outlier_colmax_kernel<ACT><<<dim3((unsigned)((K + 255) / 256), (unsigned)((M + 63) / 64)), 256, 0, st>>>(x, (int)M, (int)K, colmax);
+    outlier_columns_kernel<<<1, 1024, 0, st>>>(colmax, (int)K, threshold, flag, jlist, jcount);
+    outlier_rowquant_kernel<ACT><<<(unsigned)M, 256, 0, st>>>(x, (int)K, flag, cx, qx);
+
     p.a_bytes = kOTileN * kOBlockK;
     p.b_bytes = (uint32_t)mb * kOBlockK;
     int stages = (int)((150u * 1024u) / (p.a_bytes + p.b_bytes));      // the epilogue's tables take ~58 KB of static shared memory
@@ -389,8 +457,8 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    dim3 grid((unsigned)((N + kOTileN - 1) / kOTileN), (unsigned)((M + mb - 1) / mb));
-    kern<<<grid, kOThreads, smem, st>>>(tmap_w, tmap_x, tmap_y, x, qw, cw, cx, jlist, jcount, bias, y, p);
+    dim3 grid((unsigned)((N + kOTileN - 1) / kOTileN), (unsigned)((M + mb - 1) / mb), (unsigned)p.splits);
+    kern<<<grid, kOThreads, smem, st>>>(tmap_w, tmap_x, tmap_y, x, qw, cw, cx, jlist, jcount, bias, y, acc, counters, p);
     return cuda_status(cudaGetLastError());
 }
 
