@@ -142,13 +142,20 @@ __global__ void __launch_bounds__(128) dequant_dim0_kernel(const uint8_t* __rest
     for (int j = 0; j < 4; ++j) { p[j].s = scale[c + j]; p[j].z = zp[c + j]; p[j].rcp = CONV == kDqB ? dq_rcp(p[j].s, p[j].z) : 0.0f; }
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t r1 = min(rows, r0 + rows_per_chunk);
-#pragma unroll 4
-    for (int64_t r = r0; r < r1; ++r) {
+    auto emit = [&](int64_t r, uint32_t w) {
         const int64_t i = r * cols + c;
-        uint32_t w = load_codes4<PACKED>(q, i);
         store4<OUT>(out + i, dq_value<CONV>(byte_to_f32<0>(w), p[0], sym, off), dq_value<CONV>(byte_to_f32<1>(w), p[1], sym, off),
                     dq_value<CONV>(byte_to_f32<2>(w), p[2], sym, off), dq_value<CONV>(byte_to_f32<3>(w), p[3], sym, off));
+    };
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {                  // four rows' loads in flight
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = load_codes4<PACKED>(q, (r + k) * cols + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit(r + k, w[k]);
     }
+    for (; r < r1; ++r) emit(r, load_codes4<PACKED>(q, r * cols + c));
 }
 
 // Any shape / alignment: one element per thread.  chan(i) = 0 | i / block | i % cols.

@@ -103,6 +103,16 @@ __device__ __forceinline__ void group_params(float mn, float mx, int bits, float
 // | partial min / max
 // --------------------------------------------------------------------------
 constexpr int kWsHeaderFloats = 64;
+// one bit pattern from every 16-byte chunk of a loaded 32-element row (see mbar_arrive_after_loads)
+template <typename T>
+__device__ __forceinline__ uint32_t row_dep(const float* v) {
+    constexpr int step = 16 / (int)sizeof(T);            // elements per chunk: 4 (fp32) or 8 (16-bit)
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k += step) d ^= __float_as_uint(v[k]);
+    return d;
+}
+
 constexpr int kMaxPartialCtas = kNumSMs * 8;
 constexpr int kMaxDim0Chunks = 64;
 
@@ -372,6 +382,7 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
     using RL = RowLayout<T>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kStages], empty_bar[kStages], clc_bar;
+    __shared__ uint32_t dep_scratch[kTmaThreads / 32];           // see mbar_arrive_after_loads
     __shared__ __align__(16) uint4 clc_resp;
     __shared__ int tile_of_stage[kStages];
 
@@ -476,7 +487,7 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);     // stage can be refilled while we compute
+        if (lane == 0) mbar_arrive_after_loads(&empty_bar[s], row_dep<T>(v), &dep_scratch[warp]);     // stage can be refilled while we compute
 
         const int64_t grow = (int64_t)t * kTileRows + tid;      // global row
         const bool row_ok = grow < n_rows;
@@ -608,6 +619,7 @@ quantize_tensor_fused_kernel(const __grid_constant__ CUtensorMap tmap, const T* 
     constexpr int kTileBytes = kFRows * RL::kRowBytes;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kFMaxSlots], empty_bar[kFMaxSlots];
+    __shared__ uint32_t dep_scratch[kFThreads / 32];             // see mbar_arrive_after_loads
     __shared__ float red_mn[kFConsumers / 32], red_mx[kFConsumers / 32];
 
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -689,7 +701,7 @@ quantize_tensor_fused_kernel(const __grid_constant__ CUtensorMap tmap, const T* 
         mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
         load_row32<T>(smem + slot * kTileBytes + row_off, r, vk);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        if (lane == 0) mbar_arrive_after_loads(&empty_bar[slot], row_dep<T>(vk), &dep_scratch[warp]);
         if ((int64_t)(t0 + R + m) * kFRows + r < n_rows) {
 #pragma unroll
             for (int k = 0; k < kRowElems; ++k) { m0[k & 3] = min_nan(m0[k & 3], vk[k]); m1[k & 3] = max_nan(m1[k & 3], vk[k]); }
@@ -832,7 +844,7 @@ quantize_tensor_fused_kernel(const __grid_constant__ CUtensorMap tmap, const T* 
             float v[kRowElems];
             load_row32<T>(smem + slot * kTileBytes + row_off, r, v);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);          // refill while we compute
+            if (lane == 0) mbar_arrive_after_loads(&empty_bar[slot], row_dep<T>(v), &dep_scratch[warp]);          // refill while we compute
             quantize_row(v, t1 - 1 - K - (m2 - ns));
             m2 += kFGroups;
         }
@@ -942,6 +954,7 @@ quantize_dim0_fused_kernel(const __grid_constant__ CUtensorMap tmap, int64_t row
     constexpr float L = BITS == 8 ? 255.0f : 15.0f;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kFMaxSlots], empty_bar[kFMaxSlots];
+    __shared__ uint32_t dep_scratch[kFThreads / 32];             // see mbar_arrive_after_loads
     __shared__ uint32_t skey[kD0MaxStrips][2][32];                 // per local strip: column min / max keys
     __shared__ __align__(16) float sparam[kD0MaxStrips][3][32];    // per strip: zero point (min) | scale | rcp of 32 columns
 
@@ -1012,20 +1025,23 @@ quantize_dim0_fused_kernel(const __grid_constant__ CUtensorMap tmap, int64_t row
 #pragma unroll
         for (int j = 0; j < 4; ++j) { cmn[j] = __int_as_float(0x7f800000); cmx[j] = __int_as_float(0xff800000); }
     };
-    auto reduce_tile = [&](uint32_t tile_addr, int t) {
+    auto reduce_tile = [&](uint32_t tile_addr, int t) -> uint32_t {
         const int strip = t / tps, rb = t - strip * tps;
         if (strip - s_first != cur_ls) { flush(); cur_ls = strip - s_first; }
         const int64_t row0 = (int64_t)rb * kFRows;
+        uint32_t dep = 0;                                      // one word of every load (mbar_arrive_after_loads)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int row = 32 * gw + 4 * i + rp;
             float f[4];
             load4(tile_addr, row, f);
+            dep ^= __float_as_uint(f[0]);
             if (row0 + row < rows) {                               // rows past the end are TMA zero fill
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { cmn[j] = min_nan(cmn[j], f[j]); cmx[j] = max_nan(cmx[j], f[j]); }
             }
         }
+        return dep;
     };
     for (int i = group; i < R; i += kFGroups) {
         mbar_wait(&full_bar[i], 0);
@@ -1035,9 +1051,9 @@ quantize_dim0_fused_kernel(const __grid_constant__ CUtensorMap tmap, int64_t row
     for (int m = mfirst; m < ns; m += kFGroups) {
         const int u = m / ring, slot = R + (m - u * ring);
         mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
-        reduce_tile(smem + slot * kTileBytes, t0 + R + m);
+        const uint32_t dep = reduce_tile(smem + slot * kTileBytes, t0 + R + m);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        if (lane == 0) mbar_arrive_after_loads(&empty_bar[slot], dep, &dep_scratch[warp]);
     }
     flush();
     asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory");
@@ -1223,6 +1239,7 @@ quantize_rows_tma_multi_kernel(const __grid_constant__ MultiArgs a, int log2_lan
     using RL = RowLayout<T>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kStages], empty_bar[kStages], clc_bar;
+    __shared__ uint32_t dep_scratch[kTmaThreads / 32];           // see mbar_arrive_after_loads
     __shared__ __align__(16) uint4 clc_resp;
     __shared__ int tile_of_stage[kStages], tens_of_stage[kStages];
 
@@ -1291,7 +1308,7 @@ quantize_rows_tma_multi_kernel(const __grid_constant__ MultiArgs a, int log2_lan
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive_after_loads(&empty_bar[s], row_dep<T>(v), &dep_scratch[warp]);
 
         const int64_t grow = (int64_t)t * kTileRows + tid;
         const bool row_ok = grow < a.n_rows[ti];

@@ -124,6 +124,17 @@ n = shape[0] * shape[1]
 timeit("quantize_4bit block64 +pack, bf16 input", shape, n * 2.625, lambda i: randn(shape, i).to(torch.bfloat16),
        lambda x: Q.quantize_4bit(x, blocksize=64, packed=True), 6)
 
+# paths that the tables above do not cover: per-channel dequantize, 16-bit inputs of the single-launch kernels
+def mk_dim0(i):
+    return Q.quantize_8bit(randn(shape, i), per_channel=True)
+
+
+timeit("dequantize_8bit per_channel dim0 (A4)", shape, n * 5.0, mk_dim0, lambda t: Q.dequantize_8bit(*t), 3)
+timeit("quantize_8bit per-tensor, bf16 input (A1)", shape, n * 3.0, lambda i: randn(shape, i).to(torch.bfloat16),
+       lambda x: Q.quantize_8bit(x), 6)
+timeit("quantize_8bit per_channel dim0, bf16 input (A3)", shape, n * 3.0, lambda i: randn(shape, i).to(torch.bfloat16),
+       lambda x: Q.quantize_8bit(x, per_channel=True), 6)
+
 # NF4 (row N1): per tensor (two passes) and blockwise, quantize and dequantize
 timeit("quantize_4bit nf4 per-tensor (N1, two-pass)", shape, n * 5.0, lambda i: randn(shape, i),
        lambda x: Q.quantize_4bit(x, quant_type="nf4"), 3)
