@@ -1618,7 +1618,7 @@ static int launch_tensor_fused(const T* x, int64_t n, int64_t n_rows, uint8_t* q
     auto kern = quantize_tensor_fused_kernel<T, BITS, PACK, CONV>;
     int nslots = (224 * 1024) / kTileBytes;                      // 14 x 16 KB (+1 KB alignment) of the 227 KB an SM offers
     if (nslots > kFMaxSlots) nslots = kFMaxSlots;
-    int ring_min = (64 * 1024) / kTileBytes;                     // 64 KB in flight per SM
+    int ring_min = (128 * 1024) / kTileBytes;                    // 128 KB in flight per SM (a stage is held until its loads have returned)
     if (const char* e = getenv("QUANTA_B200_FUSED_RING")) { int v = atoi(e); if (v >= kFGroups && v < nslots) ring_min = v; }
     ring_min = (ring_min + kFGroups - 1) / kFGroups * kFGroups;
     const int smem = nslots * kTileBytes + 1024;
