@@ -25,14 +25,28 @@ class QuantizationType(Enum):
     FP8 = "fp8"
 
 
+def _jsonable(value):
+    """Tensors leave as nested lists (0-dim tensors as numbers), everything else unchanged."""
+    return value.detach().cpu().tolist() if isinstance(value, torch.Tensor) else value
+
+
+def _from_json(value):
+    """Lists come back as tensors; numbers stay numbers (so a 0-dim scale reloads as a Python float, as it
+    does in the reference)."""
+    return torch.tensor(value) if isinstance(value, list) else value
+
+
 class QuantizationState:
-    """Per-tensor / per-layer parameter tables plus a global default configuration (state.py:19-27)."""
+    """Per-tensor / per-layer parameter tables plus a global default configuration (state.py:19-27).
+    ``tensor_params``, ``layers_params`` and ``global_config`` are plain dicts, as in the reference."""
+
+    _DEFAULTS = (("default_bits", 8), ("default_scheme", QuantizationScheme.SYMMETRIC.value),
+                 ("default_type", QuantizationType.LINEAR.value))
 
     def __init__(self):
         self.tensor_params: Dict[str, Dict] = {}
         self.layers_params: Dict[str, Dict] = {}
-        self.global_config = {"default_bits": 8, "default_scheme": QuantizationScheme.SYMMETRIC.value,
-                              "default_type": QuantizationType.LINEAR.value}
+        self.global_config = dict(self._DEFAULTS)
         self._quantized_tensors: Dict[str, torch.Tensor] = {}
 
     # -- tables (state.py:29-82) --------------------------------------------------------------
@@ -51,49 +65,49 @@ class QuantizationState:
     def update_global_config(self, config_updates: Dict):
         self.global_config.update(config_updates)
 
-    # -- JSON (state.py:84-133): tensors become nested lists on the way out, lists become tensors on the way in
+    # -- JSON (state.py:84-133) ----------------------------------------------------------------
     def save_state(self, filepath: str):
-        tensors = {name: {k: (v.detach().cpu().tolist() if isinstance(v, torch.Tensor) else v) for k, v in params.items()}
-                   for name, params in self.tensor_params.items()}
-        with open(filepath, "w") as f:
-            json.dump({"tensor_params": tensors, "layers_params": self.layers_params, "global_config": self.global_config},
-                      f, indent=2)
+        document = {"tensor_params": {name: {k: _jsonable(v) for k, v in table.items()}
+                                      for name, table in self.tensor_params.items()},
+                    "layers_params": self.layers_params,
+                    "global_config": self.global_config}
+        with open(filepath, "w") as out:
+            json.dump(document, out, indent=2)
 
     def load_state(self, filepath: str):
         if not os.path.exists(filepath):
             raise FileNotFoundError(f"State file not found: {filepath}")
-        with open(filepath, "r") as f:
-            state = json.load(f)
-        self.global_config = state.get("global_config", self.global_config)
-        self.layers_params = state.get("layers_params", {})
-        for name, params in state.get("tensor_params", {}).items():
-            self.tensor_params[name] = {k: (torch.tensor(v) if isinstance(v, list) else v) for k, v in params.items()}
+        with open(filepath, "r") as src:
+            document = json.load(src)
+        self.global_config = document.get("global_config", self.global_config)
+        self.layers_params = document.get("layers_params", {})
+        for name, table in document.get("tensor_params", {}).items():
+            self.tensor_params[name] = {k: _from_json(v) for k, v in table.items()}
 
     # -- files (state.py:135-196) --------------------------------------------------------------
-    def _params_or_raise(self, tensor_name: str) -> Dict:
-        params = self.get_tensor_params(tensor_name)
-        if params is None:
+    def _require(self, tensor_name: str, need_scale: bool = False) -> Dict:
+        table = self.tensor_params.get(tensor_name)
+        if table is None:
             raise ValueError(f"No parameters found for tensor '{tensor_name}' in state")
-        return params
+        if need_scale and (table.get("scale") is None or table.get("zero_point") is None):
+            raise ValueError(f"Missing scale or zero_point for tensor '{tensor_name}'")
+        return table
 
     def save_quantized_tensor_with_state(self, tensor_name: str, q_tensor: torch.Tensor, file_path: str):
-        from ..utils.utils import save_quantized_tensor, save_quantized_tensor_torch
-        params = self._params_or_raise(tensor_name)
-        scale, zero_point = params.get("scale"), params.get("zero_point")
-        if scale is None or zero_point is None:
-            raise ValueError(f"Missing scale or zero_point for tensor '{tensor_name}'")
-        writer = save_quantized_tensor_torch if file_path.endswith(".pt") else save_quantized_tensor
-        writer(q_tensor, scale, zero_point, params, file_path)
+        from ..utils import utils as io
+        table = self._require(tensor_name, need_scale=True)
+        write = io.save_quantized_tensor_torch if file_path.endswith(".pt") else io.save_quantized_tensor
+        write(q_tensor, table["scale"], table["zero_point"], table, file_path)
 
     def load_quantized_tensor_with_state(self, tensor_name: str, file_path: str, device=None) -> torch.Tensor:
-        from ..utils.utils import load_quantized_tensor, load_quantized_tensor_torch
+        from ..utils import utils as io
         if file_path.endswith(".pt"):
-            q, scale, zero_point, params = load_quantized_tensor_torch(file_path, map_location=device)
+            q, scale, zero_point, table = io.load_quantized_tensor_torch(file_path, map_location=device)
         else:
-            q, scale, zero_point, params = load_quantized_tensor(file_path, device=device)
-        params.setdefault("scale", scale)
-        params.setdefault("zero_point", zero_point)
-        self.set_tensor_params(tensor_name, params)
+            q, scale, zero_point, table = io.load_quantized_tensor(file_path, device=device)
+        table.setdefault("scale", scale)
+        table.setdefault("zero_point", zero_point)
+        self.tensor_params[tensor_name] = table
         self._quantized_tensors[tensor_name] = q
         return q
 
@@ -101,24 +115,22 @@ class QuantizationState:
     def convert_tensor_precision(self, tensor_name: str, target_bits: int, target_type: str = "linear",
                                  target_scheme: str = None) -> torch.Tensor:
         from ..utils.utils import convert_precision
-        source = self._params_or_raise(tensor_name)
-        if tensor_name not in self._quantized_tensors:
+        source = self._require(tensor_name)
+        held = self._quantized_tensors.get(tensor_name)
+        if held is None:
             raise ValueError(f"Quantized tensor '{tensor_name}' not found in state. "
                              f"Please load the tensor first using load_quantized_tensor_with_state.")
-        q, _, _, new_params = convert_precision(self._quantized_tensors[tensor_name], source, target_bits, target_type,
-                                                target_scheme)
-        self.set_tensor_params(tensor_name, new_params)
+        q, _, _, table = convert_precision(held, source, target_bits, target_type, target_scheme)
+        self.tensor_params[tensor_name] = table
         self._quantized_tensors[tensor_name] = q
         return q
 
     def dequantize_tensor(self, tensor_name: str, q_tensor: torch.Tensor) -> torch.Tensor:
-        from .quantization import dequantize_4bit, dequantize_8bit
-        params = self._params_or_raise(tensor_name)
-        bits = params.get("bits", 8)
-        scale, zero_point = params.get("scale"), params.get("zero_point")
-        if scale is None or zero_point is None:
-            raise ValueError(f"Missing scale or zero_point for tensor '{tensor_name}'")
-        if bits not in (4, 8):
-            raise ValueError(f"Unsupported bit depth: {bits}")
-        fn = dequantize_8bit if bits == 8 else dequantize_4bit
-        return fn(q_tensor, scale, zero_point, quant_type=params.get("type", QuantizationType.LINEAR.value))
+        from . import quantization as fq
+        table = self._require(tensor_name, need_scale=True)
+        bits = table.get("bits", 8)
+        try:
+            fn = {8: fq.dequantize_8bit, 4: fq.dequantize_4bit}[bits]
+        except KeyError:
+            raise ValueError(f"Unsupported bit depth: {bits}") from None
+        return fn(q_tensor, table["scale"], table["zero_point"], quant_type=table.get("type", QuantizationType.LINEAR.value))

@@ -60,110 +60,104 @@ def tensor_bits_to_bytes(tensor, bits):
 
 def _np(v):
     import numpy as np
-    if isinstance(v, torch.Tensor):
-        return v.detach().cpu().numpy()
-    return np.asarray(v)
+    return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+
+
+def _with_suffix(path, suffix):
+    return path if path.endswith(suffix) else path + suffix
+
+
+def _count(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
 
 
 def save_quantized_tensor(q_tensor, scale, zero_point, params, file_path):
     """Write a ``.qtn`` file, byte-compatible with the reference writer (utils.py:60-108):
-    8-byte little-endian header length, JSON metadata ``{bits, scheme, type, shape, dtype}``, then the raw
-    bytes of the codes, the scale and the zero point.  Non-scalar scales (per_channel / blockwise) add
-    ``scale_shape`` / ``zero_point_shape`` to the metadata so that :func:`load_quantized_tensor` can
-    restore them (the reference's loader only reads one float each)."""
+    ``u64le(len(header)) | header JSON {bits, scheme, type, shape, dtype} | codes | scale | zero point`` (raw bytes).
+    Non-scalar scales (per_channel / blockwise) add ``scale_shape`` / ``zero_point_shape`` (and ``blocksize``) to the
+    header so that :func:`load_quantized_tensor` can restore them — the reference's loader reads one float each."""
     import json
     import os
+    import struct
+    file_path = _with_suffix(file_path, ".qtn")
     os.makedirs(os.path.dirname(os.path.abspath(file_path)), exist_ok=True)
-    if not file_path.endswith(".qtn"):
-        file_path = file_path + ".qtn"
-    q_np, s_np, z_np = _np(q_tensor), _np(scale), _np(zero_point)
-    dtype_str = str(q_tensor.dtype)
-    if dtype_str.startswith("torch."):
-        dtype_str = dtype_str[6:]
-    metadata = {"bits": params.get("bits", 8), "scheme": params.get("scheme", "symmetric"),
-                "type": params.get("type", "linear"), "shape": list(q_tensor.shape), "dtype": dtype_str}
-    if s_np.size > 1 or z_np.size > 1:
-        metadata["scale_shape"] = list(s_np.shape)
-        metadata["zero_point_shape"] = list(z_np.shape)
+    payload = [_np(q_tensor), _np(scale), _np(zero_point)]
+    header = {"bits": params.get("bits", 8), "scheme": params.get("scheme", "symmetric"),
+              "type": params.get("type", "linear"), "shape": list(q_tensor.shape),
+              "dtype": str(q_tensor.dtype).replace("torch.", "", 1)}
+    if payload[1].size > 1 or payload[2].size > 1:
+        header.update(scale_shape=list(payload[1].shape), zero_point_shape=list(payload[2].shape))
         if params.get("blocksize") is not None:
-            metadata["blocksize"] = int(params["blocksize"])
-    with open(file_path, "wb") as f:
-        header = json.dumps(metadata)
-        f.write(len(header).to_bytes(8, byteorder="little"))
-        f.write(header.encode("utf-8"))
-        f.write(q_np.tobytes())
-        f.write(s_np.tobytes())
-        f.write(z_np.tobytes())
+            header["blocksize"] = int(params["blocksize"])
+    text = json.dumps(header)
+    with open(file_path, "wb") as out:
+        out.write(struct.pack("<Q", len(text)) + text.encode("utf-8"))
+        for part in payload:
+            out.write(part.tobytes())
     return file_path
 
 
 def load_quantized_tensor(file_path, device=None):
-    """Read a ``.qtn`` file (utils.py:110-165): returns ``(q_tensor, scale, zero_point, metadata)``; files
-    written by the reference (scalar float32 scale / zero point) load exactly as the reference loads them,
-    files with ``scale_shape`` restore the parameter arrays.  ``device`` moves the result (e.g. ``"cuda"``)."""
+    """Read a ``.qtn`` file (utils.py:110-165) -> ``(q_tensor, scale, zero_point, metadata)``.  Files written by the
+    reference (scalar float32 scale / zero point) load exactly as the reference loads them; files carrying
+    ``scale_shape`` restore the parameter arrays.  ``device`` moves the result (e.g. ``"cuda"``)."""
     import json
+    import struct
     import numpy as np
-    if not file_path.endswith(".qtn"):
-        file_path = file_path + ".qtn"
-    with open(file_path, "rb") as f:
-        header_len = int.from_bytes(f.read(8), byteorder="little")
-        metadata = json.loads(f.read(header_len).decode("utf-8"))
-        shape = tuple(metadata["shape"])
-        count = int(np.prod(shape)) if len(shape) else 1
-        q = torch.from_numpy(np.frombuffer(f.read(count), dtype=np.uint8).copy().reshape(shape))
+
+    def take(src, dtype, shape):
+        n = _count(shape)
+        return np.frombuffer(src.read(n * np.dtype(dtype).itemsize), dtype=dtype).copy().reshape(shape)
+
+    with open(_with_suffix(file_path, ".qtn"), "rb") as src:
+        (header_len,) = struct.unpack("<Q", src.read(8))
+        metadata = json.loads(src.read(header_len).decode("utf-8"))
+        q = torch.from_numpy(take(src, np.uint8, tuple(metadata["shape"])))
         if "scale_shape" in metadata:
-            s_shape, z_shape = tuple(metadata["scale_shape"]), tuple(metadata["zero_point_shape"])
-            ns, nz = int(np.prod(s_shape)) if len(s_shape) else 1, int(np.prod(z_shape)) if len(z_shape) else 1
-            scale = torch.from_numpy(np.frombuffer(f.read(4 * ns), dtype=np.float32).copy().reshape(s_shape))
-            zero_point = torch.from_numpy(np.frombuffer(f.read(4 * nz), dtype=np.float32).copy().reshape(z_shape))
+            scale = torch.from_numpy(take(src, np.float32, tuple(metadata["scale_shape"])))
+            zero_point = torch.from_numpy(take(src, np.float32, tuple(metadata["zero_point_shape"])))
         else:
-            scale = torch.tensor(np.frombuffer(f.read(4), dtype=np.float32).copy().item())
-            zero_point = torch.tensor(np.frombuffer(f.read(4), dtype=np.float32).copy().item())
+            scale = torch.tensor(take(src, np.float32, ()).item())
+            zero_point = torch.tensor(take(src, np.float32, ()).item())
     if device is not None:
-        q, scale, zero_point = q.to(device), scale.to(device), zero_point.to(device)
+        q, scale, zero_point = (t.to(device) for t in (q, scale, zero_point))
     return q, scale, zero_point, metadata
 
 
 def save_quantized_tensor_torch(q_tensor, scale, zero_point, params, file_path):
     """``torch.save`` of ``{q_tensor, scale, zero_point, params}`` (utils.py:166-186)."""
-    if not file_path.endswith(".pt"):
-        file_path = file_path + ".pt"
-    torch.save({"q_tensor": q_tensor, "scale": scale, "zero_point": zero_point, "params": params}, file_path)
+    file_path = _with_suffix(file_path, ".pt")
+    torch.save(dict(q_tensor=q_tensor, scale=scale, zero_point=zero_point, params=params), file_path)
     return file_path
 
 
 def load_quantized_tensor_torch(file_path, map_location=None):
     """Inverse of :func:`save_quantized_tensor_torch` (utils.py:188-208)."""
-    if not file_path.endswith(".pt"):
-        file_path = file_path + ".pt"
-    d = torch.load(file_path, map_location=map_location, weights_only=False)
-    return d["q_tensor"], d["scale"], d["zero_point"], d["params"]
+    blob = torch.load(_with_suffix(file_path, ".pt"), map_location=map_location, weights_only=False)
+    return tuple(blob[k] for k in ("q_tensor", "scale", "zero_point", "params"))
 
 
 def convert_precision(q_tensor, source_params, target_bits, target_type="linear", target_scheme=None):
     """Dequantize with the source parameters and quantize again at ``target_bits`` / ``target_type``
     (utils.py:216-279) — both steps on the GPU, nothing leaves the device.  Returns
     ``(q, scale_or_levels, zero_point_or_bias, new_params)``."""
-    from ..functional.quantization import quantize_8bit, quantize_4bit, dequantize_8bit, dequantize_4bit
+    from ..functional import quantization as fq
+    decode = {8: fq.dequantize_8bit, 4: fq.dequantize_4bit}
+    encode = {8: fq.quantize_8bit, 4: fq.quantize_4bit}
     source_bits = source_params.get("bits", 8)
-    source_type = source_params.get("type", "linear")
-    if target_scheme is None:
-        target_scheme = source_params.get("scheme", "symmetric")
-    if source_bits == 8:
-        fp = dequantize_8bit(q_tensor, source_params.get("scale"), source_params.get("zero_point"), quant_type=source_type)
-    elif source_bits == 4:
-        fp = dequantize_4bit(q_tensor, source_params.get("scale"), source_params.get("zero_point"), quant_type=source_type)
-    else:
+    if source_bits not in decode:
         raise ValueError(f"Unsupported source bit depth: {source_bits}")
-    if target_bits == 8:
-        new_q, new_scale, new_zp = quantize_8bit(fp, quant_type=target_type)
-    elif target_bits == 4:
-        new_q, new_scale, new_zp = quantize_4bit(fp, quant_type=target_type)
-    else:
+    if target_bits not in encode:
         raise ValueError(f"Unsupported target bit depth: {target_bits}")
-    new_params = {"bits": target_bits, "type": target_type, "scheme": target_scheme, "scale": new_scale,
-                  "zero_point": new_zp, "shape": tuple(new_q.shape)}
-    return new_q, new_scale, new_zp, new_params
+    full = decode[source_bits](q_tensor, source_params.get("scale"), source_params.get("zero_point"),
+                               quant_type=source_params.get("type", "linear"))
+    q, first, second = encode[target_bits](full, quant_type=target_type)
+    scheme = target_scheme if target_scheme is not None else source_params.get("scheme", "symmetric")
+    return q, first, second, {"bits": target_bits, "type": target_type, "scheme": scheme, "scale": first,
+                              "zero_point": second, "shape": tuple(q.shape)}
 
 
 def convert_8bit_to_4bit(q_tensor, source_params, target_type="linear"):
@@ -176,9 +170,11 @@ def convert_4bit_to_8bit(q_tensor, source_params, target_type="linear"):
     return convert_precision(q_tensor, source_params, 8, target_type)
 
 
+_HARDWARE = {"cpu": (8, "linear"), "gpu": (8, "linear"), "mobile": (4, "nf4"), "edge": (4, "linear")}
+
+
 def optimize_for_target_hardware(q_tensor, source_params, target_hardware):
-    """The reference's hardware table (utils.py:309-337): cpu / gpu -> 8-bit linear, mobile -> nf4, edge -> 4-bit linear."""
-    hw = {"cpu": {"bits": 8, "type": "linear"}, "gpu": {"bits": 8, "type": "linear"},
-          "mobile": {"bits": 4, "type": "nf4"}, "edge": {"bits": 4, "type": "linear"}}
-    cfg = hw.get(target_hardware, {"bits": 8, "type": "linear"})
-    return convert_precision(q_tensor, source_params, cfg["bits"], cfg["type"])
+    """The reference's hardware table (utils.py:309-337): cpu / gpu -> 8-bit linear, mobile -> nf4, edge -> 4-bit
+    linear, anything else -> 8-bit linear."""
+    bits, kind = _HARDWARE.get(target_hardware, (8, "linear"))
+    return convert_precision(q_tensor, source_params, bits, kind)
