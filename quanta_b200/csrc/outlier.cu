@@ -47,40 +47,41 @@ __global__ void __launch_bounds__(256) outlier_colmax_kernel(const ACT* __restri
     if (c >= K) return;
     const int r0 = blockIdx.y * 64, r1 = min(M, r0 + 64);
     float mx = 0.0f;
+#pragma unroll 8
     for (int i = r0; i < r1; ++i) mx = fmaxf(mx, fabsf(ld_act(x + (int64_t)i * K + c)));
     if (gridDim.y == 1) colmax[c] = __float_as_uint(mx);        // one chunk covers every row: no merge, no memset needed
     else atomicMax(colmax + c, __float_as_uint(mx));
 }
 
-// 1b. flags and the ordered list J: one CTA, block-wide exclusive scan per 1024 columns.
+// 1b. flags and the ordered list J: one CTA, thread = a contiguous run of columns, ONE block-wide
+//     exclusive scan of the per-thread counts (two barriers in all, whatever K is).
 __global__ void __launch_bounds__(1024) outlier_columns_kernel(const unsigned int* __restrict__ colmax, int K, float threshold,
                                                                uint8_t* __restrict__ flag, int* __restrict__ jlist,
                                                                int* __restrict__ jcount) {
-    __shared__ int warp_sums[32];
-    __shared__ int base;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < K; c0 += 1024) {
-        const int c = c0 + threadIdx.x;
-        int f = 0;
-        if (c < K) {
-            f = __uint_as_float(colmax[c]) > threshold ? 1 : 0;
-            flag[c] = (uint8_t)f;
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, f);
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const int in_warp = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) warp_sums[w] = __popc(ballot);
-        __syncthreads();
-        int before = 0;
-        for (int k = 0; k < w; ++k) before += warp_sums[k];
-        const int b = base;
-        if (f) jlist[b + before + in_warp] = c;
-        __syncthreads();
-        if (threadIdx.x == 1023) base = b + before + __popc(ballot);
-        __syncthreads();
+    __shared__ int warp_counts[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int c_per = (K + 1023) / 1024;
+    const int c0 = tid * c_per, c1 = min(K, c0 + c_per);
+    int cnt = 0;
+    for (int c = c0; c < c1; ++c) {
+        const int f = __uint_as_float(colmax[c]) > threshold ? 1 : 0;
+        flag[c] = (uint8_t)f;
+        cnt += f;
     }
-    if (threadIdx.x == 0) *jcount = base;
+    int incl = cnt;                                      // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_counts[w] = incl;
+    __syncthreads();
+    int base = incl - cnt;
+    for (int k = 0; k < w; ++k) base += warp_counts[k];
+    if (cnt) {
+        for (int c = c0; c < c1; ++c) if (__uint_as_float(colmax[c]) > threshold) jlist[base++] = c;
+    }
+    if (tid == 1023) *jcount = base;
 }
 
 // ---- 2. per-row int8 codes of the non-outlier part ----------------------------
@@ -107,6 +108,50 @@ __global__ void __launch_bounds__(256) outlier_rowquant_kernel(const ACT* __rest
         float v = flag[k] ? 0.0f : __fmul_rn(ld_act(xr + k), c);
         v = fminf(fmaxf(rintf(v), -127.0f), 127.0f);
         qr[k] = (int8_t)(int)v;
+    }
+}
+
+// 2'. the same with 8 columns per thread per step (16-byte activation loads, 8-byte flag loads and code
+//     stores); needs K % 8 == 0 and 16-byte aligned rows.
+template <typename ACT>
+__global__ void __launch_bounds__(256) outlier_rowquant_vec_kernel(const ACT* __restrict__ x, int K,
+                                                                   const uint8_t* __restrict__ flag,
+                                                                   float* __restrict__ cx, int8_t* __restrict__ qx) {
+    const int i = blockIdx.x;
+    const ACT* xr = x + (int64_t)i * K;
+    const int nvec = K >> 3;
+    float am = 0.0f;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(xr) + v);
+        const uint2 f = __ldg(reinterpret_cast<const uint2*>(flag) + v);
+        const ACT* e = reinterpret_cast<const ACT*>(&d);
+        const uint8_t* fb = reinterpret_cast<const uint8_t*>(&f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!fb[k]) am = fmaxf(am, fabsf(ld_act(e + k)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = am;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) am = fmaxf(am, red[w]);
+    const float c = am == 0.0f ? 1.0f : __fmul_rn(__frcp_rn(am), 127.0f);
+    if (threadIdx.x == 0) cx[i] = c;
+    int8_t* qr = qx + (int64_t)i * K;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(xr) + v);
+        const uint2 f = __ldg(reinterpret_cast<const uint2*>(flag) + v);
+        const ACT* e = reinterpret_cast<const ACT*>(&d);
+        const uint8_t* fb = reinterpret_cast<const uint8_t*>(&f);
+        uint32_t packed[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float t = fb[k] ? 0.0f : __fmul_rn(ld_act(e + k), c);
+            t = fminf(fmaxf(rintf(t), -127.0f), 127.0f);
+            packed[k >> 2] |= ((uint32_t)(int)t & 0xFFu) << (8 * (k & 3));
+        }
+        *(reinterpret_cast<uint2*>(qr) + v) = make_uint2(packed[0], packed[1]);
     }
 }
 
@@ -424,7 +469,10 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
     }
     outlier_colmax_kernel<ACT><<<dim3((unsigned)((K + 255) / 256), (unsigned)((M + 63) / 64)), 256, 0, st>>>(x, (int)M, (int)K, colmax);
     outlier_columns_kernel<<<1, 1024, 0, st>>>(colmax, (int)K, threshold, flag, jlist, jcount);
-    outlier_rowquant_kernel<ACT><<<(unsigned)M, 256, 0, st>>>(x, (int)K, flag, cx, qx);
+    if (K % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        outlier_rowquant_vec_kernel<ACT><<<(unsigned)M, 256, 0, st>>>(x, (int)K, flag, cx, qx);
+    else
+        outlier_rowquant_kernel<ACT><<<(unsigned)M, 256, 0, st>>>(x, (int)K, flag, cx, qx);
 
     p.a_bytes = kOTileN * kOBlockK;
     p.b_bytes = (uint32_t)mb * kOBlockK;
