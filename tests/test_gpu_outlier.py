@@ -27,7 +27,7 @@ def make_x(M, K, dtype, seed, outliers=True):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(128, 128, 1), (256, 512, 16), (200, 320, 7), (512, 4096, 33), (4096, 4096, 256),
-                                   (1024, 2048, 300)])
+                                   (1024, 2048, 300), (256, 8192, 5), (384, 16384, 16)])      # the last two take the split-K path
 def test_outlier_matmul_matches_oracle(dtype, shape):
     from quanta_b200.nn import int8_outlier_matmul, rowwise_quantize_sym
     N, K, M = shape
