@@ -22,7 +22,7 @@ for (N, K, M, bits) in [(1024, 512, 33, 4), (896, 1024, 7, 8), (2048, 256, 130, 
     b = torch.randn(N, generator=g) * 0.1
     x = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
     qf = Q.quantize_4bit(w.to(dev), blocksize=64, packed=True) if bits == 4 else Q.quantize_8bit(w.to(dev), blocksize=64)
-    for fused in (False, True):
+    for fused in (False, True, "peer", "multicast"):
         lin = TensorParallelLinear(K, N, bits=bits, bias=True, compute_dtype=torch.bfloat16, fused_gather=fused)
         r0, r1 = lin.rows
         lin.load_shard(w[r0:r1].to(dev), b[r0:r1].to(dev))

@@ -91,10 +91,12 @@ for (No, Ki) in SHAPES:
     for bits in (4, 8):
         lin = TensorParallelLinear(Ki, No, bits=bits, bias=False, compute_dtype=torch.bfloat16)
         lin.load_shard(wl)
-        linf = None
+        linf = linp = None
         if world > 1:
             linf = TensorParallelLinear(Ki, No, bits=bits, bias=False, compute_dtype=torch.bfloat16, fused_gather=True)
             linf.qweight, linf.scale, linf.zero_point = lin.qweight, lin.scale, lin.zero_point
+            linp = TensorParallelLinear(Ki, No, bits=bits, bias=False, compute_dtype=torch.bfloat16, fused_gather="peer")
+            linp.qweight, linp.scale, linp.zero_point = lin.qweight, lin.scale, lin.zero_point
         for Mb in (1, 16, 64, 256):
             xb = torch.randn(Mb, Ki, device=dev).to(torch.bfloat16)
             for _ in range(3):
@@ -123,7 +125,7 @@ for (No, Ki) in SHAPES:
                 e1.record(); torch.cuda.synchronize()
                 rec["us_fused"] = round(max_over_ranks(e0.elapsed_time(e1) * 1e3 / args.reps), 2)
                 # the same 20 calls replayed from a CUDA graph: device time without the host's launch path
-                for name, layer in (("us_graph", lin), ("us_fused_graph", linf)):
+                for name, layer in (("us_graph", lin), ("us_fused_graph", linf), ("us_fused_peer_graph", linp)):
                     try:
                         side = torch.cuda.Stream()
                         side.wait_stream(torch.cuda.current_stream())
@@ -144,6 +146,7 @@ for (No, Ki) in SHAPES:
                         torch.cuda.synchronize()
             emit(rec)
         del lin, linf
+        linp = None
     del wl, q4
     torch.cuda.empty_cache()
 if rank == 0 and args.out:
