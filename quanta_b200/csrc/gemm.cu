@@ -1041,11 +1041,12 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
 
-// CUDA-core path for decode-sized batches (gemv.cu)
-bool gemv_eligible(int bits, int64_t M, int64_t K, int64_t block);
+// mma.sync weight-stream kernel for decode-sized batches (gemm_small.cu)
+bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const void* scale, const void* zp);
 template <typename ACT, int BITS>
-int gemv_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, ACT* y, int64_t M,
-                int64_t N, int64_t K, cudaStream_t st);
+int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
+                      int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
+                      cudaStream_t st);
 
 template <typename ACT, int BITS>
 static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
@@ -1054,13 +1055,9 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
                        int64_t col0 = 0) {
     void* one[1] = {y};
     if (!ys) { ys = one; n_out = 1; ldy = N; col0 = 0; }
-    {
-        // M <= 4 on the CUDA cores (gemv.cu): parity-tested, but not faster than the tensor path in round 1
-        // (both end up near 21 us on the Llama shapes), so it is opt-in: QUANTA_B200_GEMV=1
-        const char* e = getenv("QUANTA_B200_GEMV");
-        if (!nf4 && n_out == 1 && ldy == N && e && e[0] == '1' && gemv_eligible(BITS, M, K, block) && (reinterpret_cast<uintptr_t>(wq) & 15) == 0)
-            return gemv_launch<ACT, BITS>(x, wq, scale, zp, bias, y, M, N, K, st);
-    }
+    // M <= 16: the weight-stream kernel (HBM-bound regime; gemm_small.cu)
+    if (!nf4 && gemm_small_eligible(M, N, K, block, scale, zp))
+        return gemm_small_launch<ACT, BITS>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     const int n_tiles = (int)((N + kTileN - 1) / kTileN);

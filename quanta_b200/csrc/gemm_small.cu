@@ -1,0 +1,736 @@
+// W4A16 / W8A16 dequantize-then-matmul for decode-sized batches (M <= 16; rows G1/G2 of SURVEY §8):
+//     y[M,N] = x[M,K] . dequant(Wq)[N,K]^T + bias,   Wq blockwise-64 along K (convention A).
+//
+// At these batch sizes the op is a pure weight stream (5.7 us of HBM time for a
+// 4096 x 14336 W4 matrix), so the kernel is built around the stream and keeps everything else
+// off its critical path:
+//
+//   * one persistent CTA per SM: a producer warp keeps a ring of TMA stages full (SWIZZLE_128B
+//     tiles of [128 rows x 128 B] codes plus the step's [128 x 4] scale / zero-point tiles on the
+//     same mbarrier; 120-160 KB in flight per SM from the first cycle to the last), 16 consumer
+//     warps drain it (warp = 32 weight rows x one 64-K block of every step, so a B fragment read
+//     from shared memory serves two row slabs).  The (row tile, 256-K step) units are cut into
+//     equal contiguous ranges, one per CTA (stream-K), so every SM streams for the same time
+//     whatever the shape;
+//   * codes are never dequantized one by one.  LOP3 drops a nibble pair into the mantissas of
+//     the 16-bit constant 128.0 (bf16) / 1024.0 (fp16) — exact integers C + n — and the warp-level
+//     tensor-core MMA (mma.sync m16n8k16, fp32 accumulate) forms raw = sum_k (C + n_k) x_k over one
+//     64-K block; scale and zero-point are applied once per block on the accumulators:
+//         y += s * raw + (z - C s) * sum_k x_k
+//     i.e. 7 integer instructions per 8 weights + 2 FMAs per accumulator, instead of 19
+//     instructions per 8 weights for an element-wise dequantization.  The MMA's K order is free as
+//     long as both operands agree, so x is staged in the order the LOP3 pairs come out
+//     (k0,k4 | k1,k5 | k2,k6 | k3,k7) and no PRMT is needed.  8-bit codes go through
+//     PRMT -> fp32 (32768 + q) -> q -> packed 16-bit, exact as well;
+//   * x is streamed like the weights: while the consumers work on unit i, each of them fetches one
+//     16-byte chunk of unit i+2's activations, permutes it into MMA fragment order and adds it to a
+//     5-slot shared-memory ring together with the per-block sums of x (an mbarrier per slot counts
+//     the 16 warps; a slot is rewritten only after every warp has passed the unit that read it);
+//   * a CTA that covers only part of a row tile's K range stores an fp32 partial; the CTA that
+//     arrives last at the tile's counter sums the partials in a fixed order (deterministic), adds
+//     the bias and writes y — to every output buffer of a tensor-parallel call (peer-mapped
+//     buffers over NVLink).  The gpu-scope fences of that hand-over cost ~1.5 us each, so only a
+//     CTA's LAST segment publishes in line (the stream is over by then); the partial of its first
+//     segment is published by a separate warp while the consumers carry on streaming.
+//
+// The products use the exact fp32 value q*s + z of the weight (the tcgen05 path in gemm.cu rounds it
+// to the activation type first, like the reference's `.to(x.dtype)`); the difference is far inside
+// the 1e-2 tolerance of rows G1/G2.
+#include "common.cuh"
+
+#include <cstdlib>
+
+namespace quanta {
+
+constexpr int kSmRows = 128;               // weight rows per tile
+constexpr int kSmConsWarps = 16;           // warp w: rows 32 (w & 3) .. +32, block (w >> 2) of every step
+constexpr int kSmConsThreads = 32 * kSmConsWarps;
+constexpr int kSmThreads = kSmConsThreads + 64;   // + producer warp + publisher warp
+constexpr int kSmStepK = 256;              // K per stage
+constexpr int kSmMaxRing = 8;
+constexpr int kSmXDist = 2;                // x of unit i + 2 is staged while unit i is computed
+constexpr int kSmXRing = 2 * kSmXDist + 1; // a warp at unit i may run next to a warp at unit i - 2
+constexpr int kSmMaxOut = 8;
+constexpr int kSmCounterBytes = 64 * 1024; // same workspace header as gemm.cu (zero before, zero after)
+
+struct SmallParams {
+    int M, N, K;
+    int S;                  // 256-K steps per row tile
+    int n_tiles;
+    int G;                  // CTAs
+    unsigned int U;         // units = n_tiles * S
+    int m_pad;              // 8 * NB
+    int R;                  // weight ring stages
+    int ldy, col0, n_out;
+    int vec_y;              // 8-byte y stores are aligned in every output buffer
+    int dbg;                // experiment switches (QUANTA_B200_SMALL_DBG): 1 no compute, 2 no x staging, 4 no epilogue
+    uint32_t stage_bytes;   // codes + scale tile + zero-point tile
+    uint32_t code_bytes;
+    uint32_t x_off;         // x ring
+    uint32_t x_slot_bytes;  // m_pad * 512 (chunks) + NB * 128 (block sums)
+    uint32_t red_off;       // [3][4 row groups][2 slabs][NB][4][32] floats: the K quarters of a tile meet here
+    uint32_t bar_off;       // mbarriers + flags
+    void* y[kSmMaxOut];
+};
+
+template <typename ACT> struct SmTraits;
+template <> struct SmTraits<__nv_bfloat16> {
+    static constexpr uint32_t kMagic = 0x43004300u;   // bf16x2 (128 + n)
+    static constexpr float kOffset = 128.0f;
+    __device__ static __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+    __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&t);
+    }
+    __device__ static __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+        asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+};
+template <> struct SmTraits<__half> {
+    static constexpr uint32_t kMagic = 0x64006400u;   // fp16x2 (1024 + n)
+    static constexpr float kOffset = 1024.0f;
+    __device__ static __forceinline__ float to_float(__half v) { return __half2float(v); }
+    __device__ static __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
+    __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+        __half2 t = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&t);
+    }
+    __device__ static __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+        asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+};
+
+__device__ __forceinline__ uint32_t sm_and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t sm_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r;
+}
+__device__ __forceinline__ uint2 sm_lds64(uint32_t addr) {
+    uint2 v; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v;
+}
+__device__ __forceinline__ uint4 sm_lds128(uint32_t addr) {
+    uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sm_sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sm_sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float sm_lds32(uint32_t addr) {
+    float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sm_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void sm_bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sm_bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SMW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SMD_%=;\n\t"
+        "bra SMW_%=;\n\t"
+        "SMD_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sm_cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSmConsThreads) : "memory"); }
+
+// 4-bit: one 32-bit word = nibbles n0..n7 of 8 consecutive K values.  Four LOP3 (+ three shifts)
+// give the exact 16-bit pairs (C+n0, C+n4), (C+n1, C+n5), (C+n2, C+n6), (C+n3, C+n7).
+template <typename ACT>
+__device__ __forceinline__ void sm_pairs4(uint32_t w, uint32_t* p) {
+    constexpr uint32_t kM = SmTraits<ACT>::kMagic;
+    p[0] = sm_and_or(w, 0x000F000Fu, kM);
+    p[1] = sm_and_or(w >> 4, 0x000F000Fu, kM);
+    p[2] = sm_and_or(w >> 8, 0x000F000Fu, kM);
+    p[3] = sm_and_or(w >> 12, 0x000F000Fu, kM);
+}
+// 8-bit: one word = 4 codes; PRMT builds the fp32 value 32768 + q, one subtraction leaves q exactly,
+// pairs (q0, q1), (q2, q3) in natural K order.
+template <typename ACT>
+__device__ __forceinline__ void sm_pairs8(uint32_t w, uint32_t* p) {
+    float f[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        f[e] = __fadd_rn(__uint_as_float(sm_prmt(w, 0x47000000u, 0x7504u | (e << 4))), -32768.0f);
+    p[0] = SmTraits<ACT>::pack(f[0], f[1]);
+    p[1] = SmTraits<ACT>::pack(f[2], f[3]);
+}
+
+// Row of the warp's 16-row slab that MMA row `gid` (0..7; +8 for the second half) stands for, chosen so
+// that the shared-memory reads of the swizzled code tile are conflict-free: 4-bit reads 8 bytes per
+// lane (a half-warp = MMA rows 0..3 must differ in bits 1-2 of the row), 8-bit 16 bytes per lane (a
+// quarter-warp = MMA rows 2q, 2q+1 must differ in bit 2).
+template <int BITS> __device__ __forceinline__ int sm_row_of(int gid) {
+    return BITS == 4 ? (((gid & 3) << 1) | (gid >> 2)) : (((gid & 1) << 2) | (gid >> 1));
+}
+
+// CTA whose unit range [U c / G, U (c+1) / G) contains unit u
+__device__ __forceinline__ int sm_cta_of_unit(unsigned int u, const SmallParams& p) {
+    const unsigned int G = (unsigned int)p.G;
+    unsigned int c = (unsigned int)(((unsigned long long)u * G) / p.U);
+    while (c + 1 < G && p.U * (c + 1) / G <= u) ++c;
+    while (c > 0 && p.U * c / G > u) --c;
+    return (int)c;
+}
+
+// Stream-K hand-over of one tile, publishing side (one thread): gpu-scope fences around the counter
+// update; returns 1 if this CTA arrived last (and resets the counter for the next call).
+__device__ __forceinline__ int sm_publish(unsigned int* counters, int tile, int contributors) {
+    __threadfence();
+    const unsigned int old = atomicAdd(&counters[tile], 1u);
+    __threadfence();
+    const int last = (old == (unsigned int)(contributors - 1)) ? 1 : 0;
+    if (last) counters[tile] = 0u;
+    return last;
+}
+
+// Sum the partials of every contributor of `tile` in CTA order (deterministic), add the bias, write y.
+// Thread j of `nthreads` (a multiple of 32): 4 consecutive features, batch rows j / 32 + (nthreads / 32) k;
+// 8 contributors' loads in flight per thread.
+template <typename ACT>
+__device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __restrict__ bias, const float* __restrict__ partial,
+                                         int tile, int c_first, int c_last, int j, int nthreads) {
+    using T = SmTraits<ACT>;
+    const unsigned int S = (unsigned int)p.S;
+    const int n0 = tile * kSmRows;
+    const int f4 = 4 * (j & 31), gn4 = n0 + f4;
+    const size_t slot = (size_t)(kSmRows * p.m_pad);
+    float b4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && gn4 + e < p.N) ? T::to_float(bias[gn4 + e]) : 0.0f;
+    for (int m = j >> 5; m < p.M; m += nthreads >> 5) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = c_first; c0 <= c_last; c0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c <= c_last) {
+                    const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / S)) ? 0 : 1;
+                    v[u] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)c * 2 + wc) * slot + m * kSmRows + f4));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        const float o4[4] = {acc.x + b4[0], acc.y + b4[1], acc.z + b4[2], acc.w + b4[3]};
+        for (int o = 0; o < p.n_out; ++o) {
+            ACT* dst = static_cast<ACT*>(p.y[o]) + (int64_t)m * p.ldy + p.col0 + gn4;
+            if (p.vec_y && gn4 + 3 < p.N) {
+                uint2 pk;
+                pk.x = T::pack(o4[0], o4[1]);
+                pk.y = T::pack(o4[2], o4[3]);
+                *reinterpret_cast<uint2*>(dst) = pk;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (gn4 + e < p.N) dst[e] = T::from_float(o4[e]);
+            }
+        }
+    }
+}
+
+template <typename ACT, int BITS, int NB>
+__global__ void __launch_bounds__(kSmThreads, 1)
+gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
+                  const __grid_constant__ CUtensorMap tmap_z, const ACT* __restrict__ x, const ACT* __restrict__ bias,
+                  unsigned int* __restrict__ counters, float* __restrict__ partial, const __grid_constant__ SmallParams p) {
+    using T = SmTraits<ACT>;
+    extern __shared__ __align__(1024) uint8_t sm_raw[];
+    constexpr int kChunks = 8 * NB * 32;                     // 16-byte x chunks per unit
+    constexpr int kXIter = (kChunks + kSmConsThreads - 1) / kSmConsThreads;
+
+    const uint32_t smem = smem_u32(sm_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t bars = smem + p.bar_off;                  // full[R] | empty[R] | xfull[kSmXRing] | flag
+    auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
+    auto empty_bar = [&](int s) { return bars + (uint32_t)(kSmMaxRing + s) * 8u; };
+    auto xfull_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + s) * 8u; };
+    const uint32_t flag_addr = bars + (uint32_t)(2 * kSmMaxRing + kSmXRing) * 8u;
+
+    const unsigned int cta = blockIdx.x;
+    const unsigned int u0 = p.U * cta / (unsigned int)p.G, u1 = p.U * (cta + 1u) / (unsigned int)p.G;
+    const int n_units = (int)(u1 - u0);
+    const int S = p.S;
+    const int tile0 = (int)(u0 / (unsigned int)S), step0 = (int)(u0 - (unsigned int)tile0 * (unsigned int)S);
+    // the CTA's first segment is published out of line iff it is a partial one and more work follows
+    const bool first_async = step0 != 0 && (unsigned int)(tile0 + 1) * (unsigned int)S < u1;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.R; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar(s)), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar(s)), "r"(kSmConsWarps));
+        }
+        for (int s = 0; s < kSmXRing; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xfull_bar(s)), "r"(kSmConsWarps));
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kSmConsWarps) {
+        // ===== producer: keeps the ring full across tile boundaries =====
+        if (lane == 0) {
+            prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z);
+            const uint64_t pol = policy_evict_first();       // weights are streamed once
+            int slot = 0, tile = tile0, step = step0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_units; ++i) {
+                if (p.dbg & 8) break;
+                if (i >= p.R) sm_bar_wait(empty_bar(slot), ph ^ 1u);
+                const uint32_t bar = full_bar(slot);
+                const uint32_t dst = smem + (uint32_t)slot * p.stage_bytes;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.stage_bytes) : "memory");
+                const int kb = step * kSmStepK, n0 = tile * kSmRows;
+                if (BITS == 4) {
+                    sm_tma_2d(dst, &tmap_w, bar, kb / 2, n0, pol);
+                } else {
+                    sm_tma_2d(dst, &tmap_w, bar, kb, n0, pol);
+                    sm_tma_2d(dst + 16384u, &tmap_w, bar, kb + 128, n0, pol);
+                }
+                sm_tma_2d(dst + p.code_bytes, &tmap_s, bar, kb / 64, n0, pol);
+                sm_tma_2d(dst + p.code_bytes + 2048u, &tmap_z, bar, kb / 64, n0, pol);
+                if (++slot == p.R) { slot = 0; ph ^= 1u; }
+                if (++step == S) { step = 0; ++tile; }
+            }
+        }
+        return;
+    }
+    if (warp == kSmConsWarps + 1) {
+        // ===== publisher: hands over the partial of the CTA's first segment while the stream runs on =====
+        if (first_async && !(p.dbg & 4)) {
+            asm volatile("bar.sync 2, 160;" ::: "memory");   // the 4 output warps have stored the partial
+            const unsigned int tu0 = (unsigned int)tile0 * (unsigned int)S;
+            const int c_first = sm_cta_of_unit(tu0, p), c_last = sm_cta_of_unit(tu0 + (unsigned int)S - 1u, p);
+            int last = 0;
+            if (lane == 0) last = sm_publish(counters, tile0, c_last - c_first + 1);
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) sm_fixup<ACT>(p, bias, partial, tile0, c_first, c_last, lane, 32);     // rare: the others finished first
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int gid = lane >> 2, tig = lane & 3;
+    const int rg = warp & 3, kq = warp >> 2;                 // rows 32 rg .. +32, block kq
+    // rows[sl][h]: slab sl (16 rows), MMA row gid + 8 h
+    int rows[2][2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) { rows[sl][0] = (2 * rg + sl) * 16 + sm_row_of<BITS>(gid); rows[sl][1] = rows[sl][0] + 8; }
+
+    // x chunk c of a unit (c = tid + 512 it): batch row m = c / 32, block (c / 8) & 3, 8 consecutive K values
+    // 8 (c & 7) of the block -> ring slot chunk (((nb 4 + blk) 2 + j) 32 + gid 4 + tig) with
+    // nb = m / 8, gid = m & 7, tig = (c & 7) / 2, j = c & 1; a warp's B-fragment read of one
+    // (nb, blk, j) is 512 contiguous bytes.  Everything but the step is fixed per thread.
+    const ACT* xsrc[kXIter];
+    uint32_t xdst[kXIter], xsum_dst[kXIter];
+#pragma unroll
+    for (int it = 0; it < kXIter; ++it) {
+        const int c = tid + it * kSmConsThreads;
+        const int m = c >> 5, blk = (c >> 3) & 3, c8 = c & 7;
+        const int nb = m >> 3, g = m & 7, t = c8 >> 1, j = c8 & 1;
+        xsrc[it] = (c < kChunks && m < p.M) ? x + (int64_t)m * p.K + 8 * (c & 31) : nullptr;
+        xdst[it] = (uint32_t)((((nb * 4 + blk) * 2 + j) * 32 + g * 4 + t) * 16);
+        xsum_dst[it] = (uint32_t)(NB * 4096 + ((nb * 4 + blk) * 8 + g) * 4);
+    }
+    auto x_fetch = [&](int step, uint4* xv) {
+#pragma unroll
+        for (int it = 0; it < kXIter; ++it) {
+            xv[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (xsrc[it] != nullptr) xv[it] = __ldg(reinterpret_cast<const uint4*>(xsrc[it] + step * kSmStepK));
+        }
+    };
+    auto x_store = [&](int xslot_idx, const uint4* xv) {
+        const uint32_t slot = smem + p.x_off + (uint32_t)xslot_idx * p.x_slot_bytes;
+#pragma unroll
+        for (int it = 0; it < kXIter; ++it) {
+            if (tid + it * kSmConsThreads < kChunks) {       // warp-uniform: kChunks is a multiple of 256
+                uint4 v = xv[it];
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                float sum = 0.0f;
+                if (sizeof(ACT) == 2 && SmTraits<ACT>::kOffset == 128.0f) {
+                    // bf16 -> fp32 is a shift / mask
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sum += __uint_as_float(w4[q] << 16) + __uint_as_float(w4[q] & 0xFFFF0000u);
+                } else {
+                    const ACT* e = reinterpret_cast<const ACT*>(&v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sum += T::to_float(e[q]);
+                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                if (BITS == 4) {
+                    uint4 o;
+                    o.x = sm_prmt(v.x, v.z, 0x5410u);        // (x0, x4)
+                    o.y = sm_prmt(v.x, v.z, 0x7632u);        // (x1, x5)
+                    o.z = sm_prmt(v.y, v.w, 0x5410u);        // (x2, x6)
+                    o.w = sm_prmt(v.y, v.w, 0x7632u);        // (x3, x7)
+                    v = o;
+                }
+                sm_sts128(slot + xdst[it], v);
+                if ((lane & 7) == 0) sm_sts32(slot + xsum_dst[it], sum);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) sm_bar_arrive(xfull_bar(xslot_idx));
+    };
+    auto step_after = [&](int step, int d) { int s = step + d; while (s >= S) s -= S; return s; };
+
+    if (!(p.dbg & 2)) {
+        uint4 xv[kXIter];
+        for (int i = 0; i < kSmXDist && i < n_units; ++i) { x_fetch(step_after(step0, i), xv); x_store(i, xv); }
+    }
+
+    const bool do_compute = !(p.dbg & 1), do_x = !(p.dbg & 2), do_epi = !(p.dbg & 4), do_wait = !(p.dbg & 8);
+    // Per-thread shared-memory offsets (the block b = kq is fixed per warp; rows + 8 / + 16 keep the swizzle
+    // phase, so every other address of a unit is one of these plus an immediate).
+    const int r00 = rows[0][0];
+    const uint32_t w_off = BITS == 4
+        ? (uint32_t)r00 * 128u + ((((uint32_t)(2 * kq + (tig >> 1))) ^ (uint32_t)(r00 & 7)) << 4) + (uint32_t)(tig & 1) * 8u
+        : (uint32_t)(kq >> 1) * 16384u + (uint32_t)r00 * 128u + ((((uint32_t)(4 * (kq & 1) + tig)) ^ (uint32_t)(r00 & 7)) << 4);
+    const uint32_t s_off = p.code_bytes + (uint32_t)r00 * 16u + (uint32_t)kq * 4u;
+    const uint32_t xb_off = p.x_off + (uint32_t)((kq * 2) * 512 + lane * 16);
+    const uint32_t xs_off = p.x_off + (uint32_t)(NB * 4096 + (kq * 8 + 2 * tig) * 4);
+
+    float tot[2][NB][4];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) { tot[sl][nb][0] = tot[sl][nb][1] = tot[sl][nb][2] = tot[sl][nb][3] = 0.0f; }
+    int wslot = 0, xs_cur = 0, xs_ahead = kSmXDist % kSmXRing;
+    uint32_t wph = 0, xph = 0;
+    int tile = tile0, step = step0, step_ahead = step_after(step0, kSmXDist);
+    int seg_s0 = step0;                                      // first step of the current tile segment
+
+    for (int i = 0; i < n_units; ++i) {
+        uint4 xv[kXIter];
+        const bool ahead = i + kSmXDist < n_units && do_x;
+        if (ahead) x_fetch(step_ahead, xv);
+
+        if (do_wait) sm_bar_wait(full_bar(wslot), wph);
+        if (do_x) sm_bar_wait(xfull_bar(xs_cur), xph);
+
+        if (do_compute) {
+            const uint32_t sb = smem + (uint32_t)wslot * p.stage_bytes;
+            const uint32_t xs_base = smem + (uint32_t)xs_cur * p.x_slot_bytes;
+            // ---- every shared-memory read of the unit goes out first (they are ordered asm statements;
+            //      the arithmetic below is free for the compiler to interleave) ----
+            uint32_t wraw[2][2][BITS == 4 ? 2 : 4];          // [slab][row half][words]
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t wa = sb + w_off + (uint32_t)(sl * 2048 + h * 1024);
+                    if (BITS == 4) {
+                        const uint2 w = sm_lds64(wa);
+                        wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y;
+                    } else {
+                        const uint4 w = sm_lds128(wa);
+                        wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y; wraw[sl][h][BITS == 4 ? 0 : 2] = w.z; wraw[sl][h][BITS == 4 ? 1 : 3] = w.w;
+                    }
+                }
+            uint4 xb[NB][2];
+            uint2 xs2[NB];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                xb[nb][0] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096));
+                xb[nb][1] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096 + 512));
+                xs2[nb] = sm_lds64(xs_base + xs_off + (uint32_t)(nb * 128));
+            }
+            float sc[2][2], zc[2][2];
+            const float off = BITS == 4 ? T::kOffset : 0.0f;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    sc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128));
+                    zc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128 + 2048));
+                }
+            // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
+            //      are independent (2 slabs x NB accumulators) ----
+            float c[2][NB][4];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { c[sl][nb][0] = c[sl][nb][1] = c[sl][nb][2] = c[sl][nb][3] = 0.0f; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t a[2][4];                            // {row lo, row+8 lo, row hi, row+8 hi}
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (BITS == 4) {
+                        // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k
+                        const uint32_t w0 = wraw[sl][0][k >> 1] >> (8 * (k & 1)), w1 = wraw[sl][1][k >> 1] >> (8 * (k & 1));
+                        a[sl][0] = sm_and_or(w0, 0x000F000Fu, T::kMagic);
+                        a[sl][1] = sm_and_or(w1, 0x000F000Fu, T::kMagic);
+                        a[sl][2] = sm_and_or(w0 >> 4, 0x000F000Fu, T::kMagic);
+                        a[sl][3] = sm_and_or(w1 >> 4, 0x000F000Fu, T::kMagic);
+                    } else {
+                        uint32_t p0[2], p1[2];
+                        sm_pairs8<ACT>(wraw[sl][0][k], p0); sm_pairs8<ACT>(wraw[sl][1][k], p1);
+                        a[sl][0] = p0[0]; a[sl][1] = p1[0]; a[sl][2] = p0[1]; a[sl][3] = p1[1];
+                    }
+                }
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const uint4 xv4 = xb[nb][k >> 1];
+                    const uint32_t b0 = (k & 1) ? xv4.z : xv4.x, b1 = (k & 1) ? xv4.w : xv4.y;
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) T::mma(c[sl][nb], a[sl], b0, b1);
+                }
+            }
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const float z0 = __fmaf_rn(-off, sc[sl][0], zc[sl][0]), z1 = __fmaf_rn(-off, sc[sl][1], zc[sl][1]);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const float xs_a = __uint_as_float(xs2[nb].x), xs_b = __uint_as_float(xs2[nb].y);
+                    tot[sl][nb][0] = __fmaf_rn(sc[sl][0], c[sl][nb][0], __fmaf_rn(z0, xs_a, tot[sl][nb][0]));
+                    tot[sl][nb][1] = __fmaf_rn(sc[sl][0], c[sl][nb][1], __fmaf_rn(z0, xs_b, tot[sl][nb][1]));
+                    tot[sl][nb][2] = __fmaf_rn(sc[sl][1], c[sl][nb][2], __fmaf_rn(z1, xs_a, tot[sl][nb][2]));
+                    tot[sl][nb][3] = __fmaf_rn(sc[sl][1], c[sl][nb][3], __fmaf_rn(z1, xs_b, tot[sl][nb][3]));
+                }
+            }
+        }
+        // every lane's reads of the stage have been consumed by the instructions above
+        __syncwarp();
+        if (lane == 0) sm_bar_arrive(empty_bar(wslot));
+        if (++wslot == p.R) { wslot = 0; wph ^= 1u; }
+        if (++xs_cur == kSmXRing) { xs_cur = 0; xph ^= 1u; }
+
+        if (ahead) x_store(xs_ahead, xv);
+        if (++xs_ahead == kSmXRing) xs_ahead = 0;
+        if (++step_ahead == S) step_ahead = 0;
+
+        const bool seg_end = step == S - 1 || i == n_units - 1;
+        if (seg_end && do_epi) {
+            // ===== end of this CTA's segment [seg_s0, step] of `tile`: the 4 K quarters meet in shared memory =====
+            const bool whole = seg_s0 == 0 && step == S - 1;
+            const bool final_seg = i == n_units - 1;
+            const uint32_t red = smem + p.red_off + (uint32_t)(rg * (2 * NB * 4) * 128 + lane * 4);
+            const uint32_t red_group = (uint32_t)(4 * 2 * NB * 4 * 128);
+            if (kq > 0) {
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            sm_sts32(red + (uint32_t)(kq - 1) * red_group + (uint32_t)(((sl * NB + nb) * 4 + q) * 128), tot[sl][nb][q]);
+            }
+            sm_cons_sync();
+            const int n0 = tile * kSmRows;
+            if (kq == 0) {
+                // tot[sl][nb][q]: feature n0 + rows[sl][q >> 1], batch row 8 nb + 2 tig + (q & 1)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t ra = red + (uint32_t)(((sl * NB + nb) * 4 + q) * 128);
+                            tot[sl][nb][q] = ((tot[sl][nb][q] + sm_lds32(ra)) + sm_lds32(ra + red_group)) + sm_lds32(ra + 2 * red_group);
+                        }
+                if (whole) {
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int gn = n0 + rows[sl][h];
+                            const float bv = (bias != nullptr && gn < p.N) ? T::to_float(bias[gn]) : 0.0f;
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int m = 8 * nb + 2 * tig + e;
+                                    if (m < p.M && gn < p.N) {
+                                        const ACT v = T::from_float(tot[sl][nb][2 * h + e] + bv);
+                                        for (int o = 0; o < p.n_out; ++o)
+                                            static_cast<ACT*>(p.y[o])[(int64_t)m * p.ldy + p.col0 + gn] = v;
+                                    }
+                                }
+                        }
+                    }
+                } else {
+                    // this CTA's partial slot for the tile: 0 if it is the first tile the CTA touches, else 1;
+                    // layout [m][128 features]
+                    const int which = (tile == tile0) ? 0 : 1;
+                    float* mine = partial + ((size_t)cta * 2 + which) * (size_t)(kSmRows * p.m_pad);
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                __stcg(mine + (8 * nb + 2 * tig + (q & 1)) * kSmRows + rows[sl][q >> 1], tot[sl][nb][q]);
+                    if (!final_seg) {
+                        // more work follows: the publisher warp takes the hand-over from here
+                        __syncwarp();
+                        asm volatile("bar.arrive 2, 160;" ::: "memory");
+                    }
+                }
+            }
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { tot[sl][nb][0] = tot[sl][nb][1] = tot[sl][nb][2] = tot[sl][nb][3] = 0.0f; }
+            if (!whole && final_seg) {
+                // the stream is over: publish in line; the CTA that arrives last reduces every contributor's partial
+                const unsigned int tu0 = (unsigned int)tile * (unsigned int)S;
+                const int c_first = sm_cta_of_unit(tu0, p), c_last = sm_cta_of_unit(tu0 + (unsigned int)S - 1u, p);
+                sm_cons_sync();
+                if (tid == 0) {
+                    const int last = sm_publish(counters, tile, c_last - c_first + 1);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_addr), "r"(last) : "memory");
+                }
+                sm_cons_sync();
+                int last;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag_addr));
+                if (last) sm_fixup<ACT>(p, bias, partial, tile, c_first, c_last, tid, kSmConsThreads);
+            } else {
+                sm_cons_sync();                              // red is reused by the next segment
+            }
+            seg_s0 = 0;
+        }
+        if (++step == S) { step = 0; ++tile; }
+    }
+}
+
+// ---- host side --------------------------------------------------------------
+
+struct SmallTuning { int ring; int max_m; int ctas; int dbg; };
+static SmallTuning small_tuning() {
+    static const SmallTuning t = []() {
+        SmallTuning v{0, 16, 0, 0};
+        if (const char* e = getenv("QUANTA_B200_SMALL_RING")) { int s = atoi(e); if (s >= 2 && s <= kSmMaxRing) v.ring = s; }
+        if (const char* e = getenv("QUANTA_B200_SMALL_MAX_M")) { int m = atoi(e); if (m >= 0 && m <= 16) v.max_m = m; }
+        if (const char* e = getenv("QUANTA_B200_SMALL_CTAS")) { int c = atoi(e); if (c >= 1 && c <= kNumSMs) v.ctas = c; }
+        if (const char* e = getenv("QUANTA_B200_SMALL_DBG")) v.dbg = atoi(e);
+        return v;
+    }();
+    return t;
+}
+
+// The small-batch kernel serves M <= 16 with blockwise-64 parameters on K % 256 == 0.
+bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const void* scale, const void* zp) {
+    if (M > small_tuning().max_m || block != 64 || (K % kSmStepK) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) return false;
+    const int64_t n_tiles = (N + kSmRows - 1) / kSmRows;
+    if (n_tiles > kSmCounterBytes / 4) return false;
+    if ((unsigned long long)n_tiles * (unsigned long long)(K / kSmStepK) * (unsigned long long)(kNumSMs + 1) >= (1ull << 32)) return false;
+    return true;
+}
+
+template <typename ACT, int BITS, int NB>
+static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias,
+                                void* const* ys, int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K,
+                                void* workspace, size_t ws_bytes, cudaStream_t st) {
+    SmallParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.m_pad = 8 * NB;
+    p.n_tiles = (int)((N + kSmRows - 1) / kSmRows);
+    p.S = (int)(K / kSmStepK);
+    p.U = (unsigned int)p.n_tiles * (unsigned int)p.S;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = kNumSMs;
+    {
+        static int cached[64] = {0};
+        if (dev >= 0 && dev < 64) {
+            if (cached[dev] == 0) {
+                int n = 0;
+                if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+                cached[dev] = n < kNumSMs ? n : kNumSMs;     // partial slots are sized for kNumSMs
+            }
+            sms = cached[dev];
+        }
+    }
+    if (small_tuning().ctas) sms = small_tuning().ctas < sms ? small_tuning().ctas : sms;
+    p.G = (int)(p.U < (unsigned int)sms ? p.U : (unsigned int)sms);
+    p.code_bytes = BITS == 4 ? 16384u : 32768u;
+    p.stage_bytes = p.code_bytes + 4096u;
+    p.x_slot_bytes = (uint32_t)(NB * 4096 + NB * 128);
+    const uint32_t x_bytes = (uint32_t)kSmXRing * p.x_slot_bytes;
+    const uint32_t red_bytes = (uint32_t)(3 * 4 * 2 * NB * 4 * 128);
+    const uint32_t bar_bytes = 256;
+    const uint32_t budget = 226u * 1024u;
+    int ring = (int)((budget - x_bytes - red_bytes - bar_bytes) / p.stage_bytes);
+    if (ring > kSmMaxRing) ring = kSmMaxRing;
+    if (small_tuning().ring && small_tuning().ring < ring) ring = small_tuning().ring;
+    if (ring < 2) return QUANTA_EUNSUPPORTED;
+    p.R = ring;
+    p.x_off = (uint32_t)ring * p.stage_bytes;
+    p.red_off = p.x_off + x_bytes;
+    p.bar_off = p.red_off + red_bytes;
+    const int smem = (int)(p.bar_off + bar_bytes);
+    p.ldy = (int)ldy; p.col0 = (int)col0; p.n_out = n_out;
+    p.dbg = small_tuning().dbg;
+    bool aligned8 = true;
+    for (int o = 0; o < kSmMaxOut; ++o) {
+        p.y[o] = o < n_out ? ys[o] : nullptr;
+        if (o < n_out) aligned8 = aligned8 && (reinterpret_cast<uintptr_t>(ys[o]) & 7) == 0;
+    }
+    p.vec_y = (aligned8 && (ldy & 3) == 0 && (col0 & 3) == 0) ? 1 : 0;
+
+    const size_t need = (size_t)kSmCounterBytes + (size_t)p.G * 2 * kSmRows * (size_t)p.m_pad * sizeof(float) + 256;
+    if (!workspace || ws_bytes < need) return QUANTA_EWORKSPACE;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    float* partial = reinterpret_cast<float*>(ws + kSmCounterBytes);
+
+    CUtensorMap tmap_w, tmap_s, tmap_z;
+    const uint64_t wrow_bytes = (uint64_t)K * BITS / 8;
+    int rc = make_tensor_map_2d(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wq, wrow_bytes, (uint64_t)N, wrow_bytes, 128,
+                                kSmRows, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const uint64_t sstride = (uint64_t)(K / 64);
+    rc = make_tensor_map_2d(&tmap_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, scale, sstride, (uint64_t)N, sstride * 4, 4, kSmRows,
+                            CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmap_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zp, sstride, (uint64_t)N, sstride * 4, 4, kSmRows,
+                            CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+
+    auto kern = gemm_small_kernel<ACT, BITS, NB>;
+    static int smem_set[64] = {0};                           // per device (the attribute is per device)
+    if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+    }
+    kern<<<dim3((unsigned)p.G), kSmThreads, (size_t)smem, st>>>(tmap_w, tmap_s, tmap_z, x, bias, counters, partial, p);
+    return cuda_status(cudaGetLastError());
+}
+
+template <typename ACT, int BITS>
+int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
+                      int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
+                      cudaStream_t st) {
+    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+    return gemm_small_launch_nb<ACT, BITS, 2>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+}
+
+#define QUANTA_SMALL_INST(ACT, BITS)                                                                                          \
+    template int gemm_small_launch<ACT, BITS>(const ACT*, const uint8_t*, const float*, const float*, const ACT*, void* const*, \
+                                              int, int64_t, int64_t, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t);
+QUANTA_SMALL_INST(__nv_bfloat16, 4)
+QUANTA_SMALL_INST(__nv_bfloat16, 8)
+QUANTA_SMALL_INST(__half, 4)
+QUANTA_SMALL_INST(__half, 8)
+
+}  // namespace quanta

@@ -15,6 +15,7 @@ ap.add_argument("--out", default=None)
 ap.add_argument("--ms", default="1,8,16,32,64,128,256")
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--formats", default="4,8", help="comma list of 4, 8, nf4")
+ap.add_argument("--shapes", default="4096x14336,14336x4096")
 args = ap.parse_args()
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 try:
@@ -24,7 +25,7 @@ except Exception:
     HBM, TF, TFS = 6650.0, 1590.0, 1400.0
 dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
 lines = []
-for (N, K) in ((4096, 14336), (14336, 4096)):
+for (N, K) in [tuple(int(v) for v in sh.split('x')) for sh in args.shapes.split(',')]:
     for fmt in args.formats.split(","):
         nf4 = fmt == "nf4"
         bits = 4 if nf4 else int(fmt)
