@@ -67,7 +67,14 @@ QUANTA_API const char* quanta_error_string(int code);
  * call leaves them zero (allocate the buffer zero-filled, once).  The same
  * holds for the first 256 bytes of the QUANTA_OP_QUANTIZE_AFFINE /
  * QUANTA_OP_BACKEND_QUANTIZE workspace (grid-barrier counters of the
- * single-launch per-tensor kernel): keep that buffer for these entries only.  */
+ * single-launch per-tensor kernel): keep that buffer for these entries only.
+ * Bytes 48-55 of that header are the one exception to "zero": they may hold the
+ * device-visible address of a host-mapped int32 (cudaHostAlloc) error flag.  If
+ * the grid barrier of a call cannot complete (stale counters, grid not
+ * co-resident) the kernel gives up after ~1 s, stores 1 to that flag, leaves the
+ * counters zero and finishes (the outputs of that call are undefined); the host
+ * checks the flag before its next call.  With no flag registered the time-out is
+ * silent.                                                                     */
 QUANTA_API size_t quanta_workspace_bytes(int op, int64_t rows, int64_t cols);
 
 /* ---- convention A: Quanta/functional/quantization.py "linear" -------------

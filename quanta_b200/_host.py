@@ -40,19 +40,31 @@ def workspace(device, nbytes):
 
 
 _quantize_workspaces = {}
+_ERRPTR_BYTES = slice(48, 56)          # include/quanta_b200.h: address of the host-mapped error flag
 
 
 def quantize_workspace(device, nbytes):
     """Per (device, stream) workspace of the quantize entries.  Its header holds the grid-barrier
-    counters of the single-launch per-tensor kernel, which must be zero before the first call and
-    are left zero by every call (include/quanta_b200.h): zero-initialised once, never shared with
-    other kernels' scratch."""
+    counters of the single-launch per-tensor / per-channel kernels, which must be zero before the
+    first call and are left zero by every call (include/quanta_b200.h): zero-initialised once, never
+    shared with other kernels' scratch.  A pinned host int32 is registered in the header as the
+    kernels' error flag: if a grid barrier timed out in an earlier call on this workspace, the header
+    is re-zeroed and QuantaError is raised here, before the next launch."""
     key = (device.index, stream_ptr(device))
-    buf = _quantize_workspaces.get(key)
-    if buf is None or buf.numel() < nbytes:
+    rec = _quantize_workspaces.get(key)
+    if rec is not None and int(rec["flag"][0]) != 0:
+        rec["flag"].zero_()
+        rec["buf"][:256].zero_()
+        rec["buf"][_ERRPTR_BYTES].view(torch.int64).fill_(rec["flag"].data_ptr())
+        raise _lib.QuantaError("an earlier quantize call on this stream timed out at its grid barrier (its outputs are "
+                               "undefined); the workspace header has been reset — repeat the call")
+    if rec is None or rec["buf"].numel() < nbytes:
+        flag = rec["flag"] if rec is not None else torch.zeros(1, dtype=torch.int32).pin_memory()
         buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
-        _quantize_workspaces[key] = buf
-    return buf
+        buf[_ERRPTR_BYTES].view(torch.int64).fill_(flag.data_ptr())      # pinned host memory is device-visible (UVA)
+        rec = {"buf": buf, "flag": flag}
+        _quantize_workspaces[key] = rec
+    return rec["buf"]
 
 
 _gemm_workspaces = {}

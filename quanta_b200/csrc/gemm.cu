@@ -957,7 +957,7 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     if ((unsigned long long)tiles * (unsigned long long)p.S * (unsigned long long)(kNumSMs + 1) >= (1ull << 32)) return QUANTA_EUNSUPPORTED;
     p.U = (unsigned int)tiles * (unsigned int)p.S;
     p.G = choose_units(tiles, p.S, mb, BITS == 4 ? 16384 : 32768, CG);
-    if (const char* e = getenv("QUANTA_B200_GEMM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= kNumSMs / CG && (unsigned int)v <= p.U) p.G = v; }
+    { const int v = env_int("QUANTA_B200_GEMM_CTAS", 0); if (v >= 1 && v <= kNumSMs / CG && (unsigned int)v <= p.U) p.G = v; }
     p.x_kb_bytes = (uint32_t)(mb / CG) * 128u;              // this CTA's rows of one 64-K block
     p.xkb = p.x_kb_bytes <= 8192u ? 4 : (p.x_kb_bytes <= 16384u ? 2 : 1);    // activation slots of at most 32 KB
     p.x_slot_bytes = p.x_kb_bytes * (uint32_t)p.xkb;
@@ -1010,7 +1010,7 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     }
     p.vec_store = (aligned8 && (p.ldy & 3) == 0 && (p.col0 & 3) == 0) ? 1 : 0;
     p.y_tma = (aligned16 && (p.ldy & 7) == 0) ? 1 : 0;
-    if (const char* e = getenv("QUANTA_B200_GEMM_YTMA")) { if (atoi(e) == 0) p.y_tma = 0; }
+    if (env_int("QUANTA_B200_GEMM_YTMA", 1) == 0) p.y_tma = 0;
     if (p.y_tma) {
         // window [M, col0 + N] of each buffer: features past this call's columns are clipped by the map
         for (int o = 0; o < p.n_out; ++o) {
@@ -1021,12 +1021,7 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     }
     auto kern = gemm_wna16_kernel<ACT, BITS, CG, NOUT>;
     const int smem = (int)(p.x_ring_off + (uint32_t)p.x_stages * p.x_slot_bytes + 1024);
-    static int smem_set = 0;           // per instantiation
-    if (smem > smem_set) {             // static __shared__ (barriers) also counts against the 227 KB opt-in limit
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(p.G * CG));
     cfg.blockDim = dim3(kGemmThreads);
@@ -1061,12 +1056,11 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     const int n_tiles = (int)((N + kTileN - 1) / kTileN);
-    // CTA pairs (tcgen05 cta_group::2: one 256-feature MMA per pair, each CTA loads half of the
-    // activation rows) are implemented and parity-tested but measured 10-25 % slower than single
-    // CTAs on the Llama shapes in round 1 (later pipeline start, tighter coupling of the two
-    // dequant pipelines), so they are opt-in: QUANTA_B200_GEMM_CG=2.
-    int cg = 1;
-    if (const char* e = getenv("QUANTA_B200_GEMM_CG")) { int v = atoi(e); if (v == 1 || (v == 2 && n_tiles >= 2)) cg = v; }
+    // CTA pairs (tcgen05 cta_group::2: one 256-feature MMA per pair, each CTA loads half of the activation
+    // rows) are written into the kernel (template parameter CG) but measured 10-25 % slower than single CTAs in
+    // round 1 (later pipeline start, the two dequant pipelines are coupled through one A-full barrier), so only
+    // CG = 1 is instantiated.
+    const int cg = 1;
     const int mb_step = 16 * cg;                             // each CTA of a pair holds mb / 2 rows, a multiple of 16
     int mb = (int)((M + mb_step - 1) / mb_step * mb_step);
     if (mb > 256) mb = 256;
@@ -1081,21 +1075,17 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     // a second MMA-issuing warp (even / odd stages) is implemented but measured no faster: the body is
     // bound by the dequant groups, not by the issuer (QUANTA_B200_GEMM_NMMA=2 enables it)
     p.nmma = 1;
-    if (const char* e = getenv("QUANTA_B200_GEMM_NMMA")) { int v = atoi(e); if (v == 2 && p.nacc >= 2) p.nmma = 2; }
+    if (env_int("QUANTA_B200_GEMM_NMMA", 1) == 2 && p.nacc >= 2) p.nmma = 2;
     p.dbg = 0;
     p.nf4 = nf4;
     p.n_out = n_out; p.ldy = (int)ldy; p.col0 = (int)col0;
-    if (const char* e = getenv("QUANTA_B200_GEMM_DBG")) p.dbg = atoi(e);
+    p.dbg = env_int("QUANTA_B200_GEMM_DBG", 0);
     p.scale_stride = (int)(K / block);
     int bs = 0; while ((int64_t)(kBlockK << bs) < block) ++bs;
     p.block_shift = bs;
     p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
               ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
-    if (n_out > 1) {
-        if (cg == 2) return gemm_launch_cg<ACT, BITS, 2, kMaxOut>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
-        return gemm_launch_cg<ACT, BITS, 1, kMaxOut>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
-    }
-    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+    if (n_out > 1) return gemm_launch_cg<ACT, BITS, 1, kMaxOut>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
     return gemm_launch_cg<ACT, BITS, 1, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
 }
 

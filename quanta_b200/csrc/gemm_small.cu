@@ -707,12 +707,7 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     if (rc) return rc;
 
     auto kern = gemm_small_kernel<ACT, BITS, NB>;
-    static int smem_set[64] = {0};                           // per device (the attribute is per device)
-    if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 64) smem_set[dev] = smem;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     kern<<<dim3((unsigned)p.G), kSmThreads, (size_t)smem, st>>>(tmap_w, tmap_s, tmap_z, x, bias, counters, partial, p);
     return cuda_status(cudaGetLastError());
 }

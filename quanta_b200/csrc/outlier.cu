@@ -459,7 +459,7 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
     if (nk_all >= 64 && (size_t)M * (size_t)N * 4 <= kOAccBytes && tiles * 4 <= (int64_t)kOCounterBytes) {
         while (splits < 16 && tiles * (splits * 2) <= kNumSMs && nk_all / (splits * 2) >= 4) splits *= 2;
     }
-    if (const char* e = getenv("QUANTA_B200_OUTLIER_SPLITS")) { int v = atoi(e); if (v == 1) splits = 1; }
+    if (env_int("QUANTA_B200_OUTLIER_SPLITS", 0) == 1) splits = 1;
     p.splits = splits;
     if (splits > 1 || M > 64) {
         size_t clear = (size_t)K * 4;
@@ -499,12 +499,7 @@ static int outlier_launch(const ACT* x, const int8_t* qw, const float* cw, float
     }
     auto kern = int8_gemm_kernel<ACT>;
     const int smem = (int)(p.stages * (p.a_bytes + p.b_bytes) + kOEpiBytes + 1024);
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     dim3 grid((unsigned)((N + kOTileN - 1) / kOTileN), (unsigned)((M + mb - 1) / mb), (unsigned)p.splits);
     kern<<<grid, kOThreads, smem, st>>>(tmap_w, tmap_x, tmap_y, x, qw, cw, cx, jlist, jcount, bias, y, acc, counters, p);
     return cuda_status(cudaGetLastError());

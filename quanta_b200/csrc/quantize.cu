@@ -592,6 +592,24 @@ constexpr int kFConsumers = kFRows * kFGroups;
 constexpr int kFThreads = kFConsumers + 32;
 constexpr int kFMaxSlots = 32;
 constexpr int kWsArriveIdx = 8, kWsDoneIdx = 9;   // grid-barrier counters (ints) in the workspace header
+constexpr int kWsErrPtrIdx = 12;                  // ints 12-13: address of a host-mapped int32 error flag (0 = none)
+constexpr unsigned int kBarrierSpinLimit = 1u << 22;      // ~1 s of polling; a healthy barrier takes microseconds
+
+// The grid barrier did not complete (the header was not zero before the call, or the grid is not co-resident).
+// Instead of killing the context, report through the caller's host-mapped flag (include/quanta_b200.h), leave
+// the counters zero for the next call and carry on: the results of THIS call are garbage, the host wrapper
+// raises on its next entry.
+__device__ __noinline__ void barrier_timeout(float* ws) {
+    unsigned int* h = reinterpret_cast<unsigned int*>(ws);
+    const unsigned long long flag = *reinterpret_cast<volatile unsigned long long*>(h + kWsErrPtrIdx);
+    if (flag != 0ull) {
+        *reinterpret_cast<volatile int*>(flag) = 1;
+        __threadfence_system();
+    }
+    *reinterpret_cast<volatile unsigned int*>(h + kWsArriveIdx) = 0u;
+    *reinterpret_cast<volatile unsigned int*>(h + kWsDoneIdx) = 0u;
+    __threadfence();
+}
 
 template <typename T>
 __device__ __forceinline__ void load_row32(uint32_t row_addr, int r, float* v) {
@@ -744,7 +762,7 @@ quantize_tensor_fused_kernel(const __grid_constant__ CUtensorMap tmap, const T* 
             for (;;) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
                 if (seen >= (unsigned int)G) break;
-                if (++spins > (1u << 26)) __trap();    // workspace header was not zero, or the grid is not co-resident
+                if (++spins > kBarrierSpinLimit) { barrier_timeout(ws); break; }
             }
         }
         __syncwarp();
@@ -1074,7 +1092,7 @@ quantize_dim0_fused_kernel(const __grid_constant__ CUtensorMap tmap, int64_t row
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
             if (seen >= (unsigned int)G) break;
-            if (++spins > (1u << 26)) __trap();
+            if (++spins > kBarrierSpinLimit) { barrier_timeout(ws); break; }
         }
         __threadfence();
     }
@@ -1498,33 +1516,6 @@ __global__ void __launch_bounds__(256) quantize_block_generic_kernel(const T* __
 // --------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------
-EncodeTiledFn get_encode_tiled() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-int make_tensor_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, size_t elem_bytes, const void* base,
-                       uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
-                       uint32_t box_outer, CUtensorMapSwizzle swizzle) {
-    EncodeTiledFn enc = get_encode_tiled();
-    if (!enc) return QUANTA_EDRIVER;
-    (void)elem_bytes;
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {pitch_bytes};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? QUANTA_OK : QUANTA_EDRIVER;
-}
-
 template <typename T> struct TmaType;
 template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
 template <> struct TmaType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
@@ -1555,12 +1546,7 @@ static int launch_rows_tma_impl(const CUtensorMap& tmap, int64_t n_rows, int lan
     using RL = RowLayout<T>;
     auto kern = quantize_rows_tma_kernel<T, BITS, PACK, CONV, BLOCKWISE, DYN>;
     const int smem = kStages * RL::kTileBytes + 1024;
-    static bool attr_set = false;      // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
     // DYN: one CTA per tile; resident CTAs steal the not-yet-launched ones (cluster launch control)
     const unsigned grid = DYN ? (unsigned)n_tiles : (unsigned)grid_for_tiles(n_tiles);
@@ -1619,15 +1605,10 @@ static int launch_tensor_fused(const T* x, int64_t n, int64_t n_rows, uint8_t* q
     int nslots = (224 * 1024) / kTileBytes;                      // 14 x 16 KB (+1 KB alignment) of the 227 KB an SM offers
     if (nslots > kFMaxSlots) nslots = kFMaxSlots;
     int ring_min = (128 * 1024) / kTileBytes;                    // 128 KB in flight per SM (a stage is held until its loads have returned)
-    if (const char* e = getenv("QUANTA_B200_FUSED_RING")) { int v = atoi(e); if (v >= kFGroups && v < nslots) ring_min = v; }
+    { const int v = env_int("QUANTA_B200_FUSED_RING", 0); if (v >= kFGroups && v < nslots) ring_min = v; }
     ring_min = (ring_min + kFGroups - 1) / kFGroups * kFGroups;
     const int smem = nslots * kTileBytes + 1024;
-    static bool attr_set = false;      // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     const int64_t n_tiles = (n_rows + kFRows - 1) / kFRows;
     cudaLaunchConfig_t cfg = {};
     const int sms = sm_count();
@@ -1640,7 +1621,7 @@ static int launch_tensor_fused(const T* x, int64_t n, int64_t n_rows, uint8_t* q
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (const char* e = getenv("QUANTA_B200_FUSED_COOP")) { if (atoi(e) == 0) cfg.numAttrs = 0; }
+    if (env_int("QUANTA_B200_FUSED_COOP", 1) == 0) cfg.numAttrs = 0;
     return cuda_status(cudaLaunchKernelEx(&cfg, kern, tmap, x, n, n_rows, nslots, ring_min, q, scale, zp, ws));
 }
 
@@ -1679,12 +1660,7 @@ static int launch_dim0_fused(const T* x, int64_t rows, int64_t cols, uint8_t* q,
     int ring_min = (64 * 1024) / kTileBytes;
     ring_min = (ring_min + kFGroups - 1) / kFGroups * kFGroups;
     const int smem = nslots * kTileBytes + kFGroups * kFRows * 32 + 1024;      // + one staging tile per group
-    static bool attr_set = false;      // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)G);
     cfg.blockDim = dim3(kFThreads);
@@ -1695,7 +1671,7 @@ static int launch_dim0_fused(const T* x, int64_t rows, int64_t cols, uint8_t* q,
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (const char* e = getenv("QUANTA_B200_FUSED_COOP")) { if (atoi(e) == 0) cfg.numAttrs = 0; }
+    if (env_int("QUANTA_B200_FUSED_COOP", 1) == 0) cfg.numAttrs = 0;
     return cuda_status(cudaLaunchKernelEx(&cfg, kern, tmap, rows, cols, geo, nslots, ring_min, q, scale, zp, ws));
 }
 
@@ -1825,12 +1801,7 @@ static int quantize_block_batch_t(const void* const* xs, const int64_t* numels, 
     const bool shape_ok = block % kRowElems == 0 && is_pow2(block / kRowElems) && block <= 1024;
     auto kern = quantize_rows_tma_multi_kernel<T, BITS, PACK>;
     const int smem = kStages * RL::kTileBytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     MultiArgs args;
     args.count = 0;
     args.tile_base[0] = 0;

@@ -101,6 +101,8 @@ def _quantize_nf4(tensor, blocksize, packed):
     B = 0 if blocksize is None else int(blocksize)
     if B and n % B:
         raise ValueError(f"numel ({n}) must be a multiple of blocksize ({blocksize})")
+    if B and (B < 16 or B > 512 or (B & (B - 1))):
+        raise ValueError(f"NF4 blocksize must be 16 * 2^j <= 512 (got {blocksize}); the affine formats take any block size")
     with torch.cuda.device(dev):
         q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
         absmax = torch.empty(n // B if B else 1, dtype=torch.float32, device=dev)
@@ -123,10 +125,14 @@ def _dequantize_nf4(q_tensor, absmax, blocksize, packed, shape, out_dtype):
     absmax = torch.as_tensor(absmax, dtype=torch.float32, device=dev).reshape(-1).contiguous()
     out_shape = (torch.Size(shape) if shape is not None else torch.Size([q.numel() * 2])) if packed else q.shape
     n = out_shape.numel()
+    if packed and q.numel() != (n + 1) // 2:
+        raise ValueError(f"packed codes hold {q.numel()} bytes, shape {tuple(out_shape)} needs {(n + 1) // 2}")
     out = torch.empty(out_shape, dtype=out_dtype, device=dev)
     if n == 0:
         return out
     B = 0 if blocksize is None else int(blocksize)
+    if B and (B < 16 or B > 512 or (B & (B - 1))):
+        raise ValueError(f"NF4 blocksize must be 16 * 2^j <= 512 (got {blocksize}); the affine formats take any block size")
     if (B and absmax.numel() != n // B) or (not B and absmax.numel() != 1):
         raise ValueError("absmax does not match blocksize")
     with torch.cuda.device(dev):
@@ -321,6 +327,9 @@ def _dequantize_linear(q_tensor, scale, zero_point, blocksize, packed, shape, ou
     else:
         out_shape = q.shape
     n = out_shape.numel()
+    if packed and q.numel() != (n + 1) // 2:
+        # a wrong ``shape`` would make the kernel read past the packed buffer
+        raise ValueError(f"packed codes hold {q.numel()} bytes, shape {tuple(out_shape)} needs {(n + 1) // 2}")
     if n == 0:
         return torch.empty(out_shape, dtype=out_dtype, device=dev)
     ns = scale.numel()

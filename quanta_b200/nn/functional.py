@@ -6,6 +6,30 @@ import torch
 from .. import _host, _lib
 
 
+def _check_weight_args(x, wq, params, N, K, bits, blocksize, what):
+    """The kernels read ``wq`` as bytes and every parameter tensor as float32 through raw pointers: anything
+    else (a buffer that ``module.half()`` cast to 16 bits, another device, a strided view, the wrong number
+    of blocks) would be silently wrong and read out of bounds — refuse it here."""
+    if blocksize <= 0 or K % blocksize:
+        raise ValueError(f"{what}: in_features ({K}) must be a multiple of blocksize ({blocksize})")
+    if not isinstance(wq, torch.Tensor) or wq.dtype != torch.uint8:
+        raise TypeError(f"{what}: quantized weight must be a uint8 tensor")
+    if wq.device != x.device or not wq.is_contiguous():
+        raise ValueError(f"{what}: quantized weight must be contiguous and on {x.device}")
+    if wq.numel() != N * K * bits // 8:
+        raise ValueError(f"{what}: quantized weight holds {wq.numel()} bytes, expected {N * K * bits // 8} "
+                         f"([{N}, {K}] at {bits} bits)")
+    for name, t in params:
+        if not isinstance(t, torch.Tensor) or t.dtype != torch.float32:
+            raise TypeError(f"{what}: {name} must be a float32 tensor (got "
+                            f"{getattr(t, 'dtype', type(t).__name__)}); quantization parameters are never cast with the module")
+        if t.device != x.device or not t.is_contiguous():
+            raise ValueError(f"{what}: {name} must be contiguous and on {x.device}")
+        if t.numel() != N * K // blocksize:
+            raise ValueError(f"{what}: {name} holds {t.numel()} values, expected {N * K // blocksize} "
+                             f"(one per block of {blocksize})")
+
+
 def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features=None, in_features=None):
     """y = x @ dequant(Wq).T + bias on the tcgen05 tensor cores.
 
@@ -24,6 +48,9 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
     N = out_features if out_features is not None else (wq.shape[0] if wq.dim() == 2 else None)
     if N is None:
         raise ValueError("out_features is required for flat packed weights")
+    if bits not in (4, 8):
+        raise ValueError("bits must be 4 or 8")
+    _check_weight_args(x, wq, (("scale", scale), ("zero_point", zp)), N, K, bits, blocksize, "linear_wna16")
     x2 = x.reshape(-1, K)
     if not x2.is_contiguous():
         x2 = x2.contiguous()
@@ -32,7 +59,7 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
     y = torch.empty((M, N), dtype=x.dtype, device=dev)
     if M == 0:
         return y.reshape(*x.shape[:-1], N)
-    if bias is not None:
+    if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     with torch.cuda.device(dev):
         ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
@@ -63,8 +90,9 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
     ptrs, ldy = outs
     if M == 0 or N == 0:
         return
+    _check_weight_args(x, wq, (("scale", scale), ("zero_point", zp)), N, K, bits, blocksize, "linear_wna16_scatter")
     dev = x.device
-    if bias is not None:
+    if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     with torch.cuda.device(dev):
@@ -91,6 +119,7 @@ def linear_nf4a16(x, wq, absmax, bias=None, blocksize=64, out_features=None, in_
     N = out_features if out_features is not None else (wq.shape[0] if wq.dim() == 2 else None)
     if N is None:
         raise ValueError("out_features is required for flat packed weights")
+    _check_weight_args(x, wq, (("absmax", absmax),), N, K, 4, blocksize, "linear_nf4a16")
     x2 = x.reshape(-1, K)
     if not x2.is_contiguous():
         x2 = x2.contiguous()
@@ -99,7 +128,7 @@ def linear_nf4a16(x, wq, absmax, bias=None, blocksize=64, out_features=None, in_
     y = torch.empty((M, N), dtype=x.dtype, device=dev)
     if M == 0:
         return y.reshape(*x.shape[:-1], N)
-    if bias is not None:
+    if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     with torch.cuda.device(dev):
         ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
@@ -137,6 +166,10 @@ def int8_outlier_matmul(x, qw, cw, threshold=6.0, bias=None):
     if qw.dtype != torch.int8 or qw.dim() != 2:
         raise TypeError("qw must be an int8 [N, K] tensor")
     N, K = qw.shape
+    if qw.device != x.device or not qw.is_contiguous():
+        raise ValueError(f"qw must be contiguous and on {x.device}")
+    if not isinstance(cw, torch.Tensor) or cw.dtype != torch.float32 or cw.numel() != N or cw.device != x.device or not cw.is_contiguous():
+        raise TypeError(f"cw must be a contiguous float32 tensor of {N} row multipliers on {x.device}")
     if x.shape[-1] != K:
         raise ValueError(f"x has {x.shape[-1]} features, weight expects {K}")
     x2 = x.reshape(-1, K)
@@ -147,7 +180,7 @@ def int8_outlier_matmul(x, qw, cw, threshold=6.0, bias=None):
     y = torch.empty((M, N), dtype=x.dtype, device=dev)
     if M == 0:
         return y.reshape(*x.shape[:-1], N)
-    if bias is not None:
+    if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     with torch.cuda.device(dev):
         ws = _host.workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_INT8_OUTLIER, M, K))

@@ -23,8 +23,51 @@ from ..functional.quantization import quantize_4bit, quantize_8bit, dequantize_4
 from .functional import linear_wna16, linear_nf4a16, int8_outlier_matmul, rowwise_quantize_sym
 
 
+_QUANT_BUFFERS = ("qweight", "scale", "zero_point", "qweight_rowwise", "row_scale")
+_FLOAT32_BUFFERS = ("scale", "zero_point", "row_scale")
+
+
 class _QuantLinearBase(nn.Module):
     bits = 8
+
+    # ---- the quantization parameters are float32 whatever the module is cast to -------------------
+    def _apply(self, fn, *args, **kwargs):
+        """``module.half()`` / ``.to(torch.bfloat16)`` cast every floating-point buffer; the kernels read
+        scale / zero_point / row_scale as float32, so they are cast back (device moves are kept)."""
+        out = super()._apply(fn, *args, **kwargs)
+        for name in _FLOAT32_BUFFERS:
+            buf = getattr(self, name, None)
+            if isinstance(buf, torch.Tensor) and buf.dtype != torch.float32:
+                setattr(self, name, buf.to(torch.float32))
+        return out
+
+    # ---- checkpoints: a quantized layer saves and reloads through state_dict ------------------------
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """A fresh module registers the quantized buffers as None and owns a full-size float weight; a quantized
+        checkpoint holds the buffers and an empty weight.  Materialise whatever the checkpoint carries before the
+        stock loader copies it in (which then sees matching shapes)."""
+        quantized = False
+        for name in _QUANT_BUFFERS:
+            key = prefix + name
+            if key in state_dict and name in self._buffers:
+                src = state_dict[key]
+                cur = self._buffers[name]
+                if cur is None or cur.shape != src.shape or cur.dtype != src.dtype:
+                    dev = self.weight.device if self.weight.numel() else (cur.device if cur is not None else src.device)
+                    self._buffers[name] = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                quantized = True
+        wkey = prefix + "weight"
+        if wkey in state_dict and state_dict[wkey].shape != self.weight.shape:
+            w = state_dict[wkey]
+            if quantized and w.numel() == 0:        # quantized checkpoint: the float weight is gone
+                self.weight = nn.Parameter(torch.empty(0, device=self.weight.device, dtype=w.dtype), requires_grad=False)
+            elif w.dim() == 2 and tuple(w.shape) == (self.out_features, self.in_features):
+                # float checkpoint into a module that was already quantized: take the weight, drop the stale codes
+                self.weight = nn.Parameter(torch.empty_like(w, device=self.weight.device), requires_grad=False)
+                for name in _QUANT_BUFFERS:
+                    if name in self._buffers and prefix + name not in state_dict:
+                        self._buffers[name] = None
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
     def _init_common(self, in_features, out_features, bias, blocksize):
         self.in_features = in_features
@@ -87,13 +130,27 @@ class _QuantLinearBase(nn.Module):
         return dequantize_8bit(self.qweight.reshape(shape), self.scale, self.zero_point, blocksize=self.blocksize,
                                out_dtype=dtype)
 
+    def _bias_as(self, dtype, device):
+        """The bias in the compute dtype, converted once per (dtype, device, bias version) instead of on every forward."""
+        b = self.bias
+        if b is None:
+            return None
+        if b.dtype == dtype and b.device == device and b.is_contiguous():
+            return b
+        key = (dtype, device, b._version, b.data_ptr())
+        cache = self.__dict__.get("_bias_cache")
+        if cache is None or cache[0] != key:
+            cache = (key, b.detach().to(device=device, dtype=dtype).contiguous())
+            self.__dict__["_bias_cache"] = cache
+        return cache[1]
+
     def _forward_quantized(self, x, compute_dtype):
         if self.qweight is None:
             if not self.weight.is_cuda:
                 raise RuntimeError("quanta_b200 layers run on CUDA only: move the module to a GPU first")
             self.quantize_()
         xin = x if x.dtype == compute_dtype else x.to(compute_dtype)
-        y = linear_wna16(xin, self.qweight, self.scale, self.zero_point, self.bias, bits=self.bits,
+        y = linear_wna16(xin, self.qweight, self.scale, self.zero_point, self._bias_as(compute_dtype, x.device), bits=self.bits,
                          blocksize=self.blocksize, out_features=self.out_features, in_features=self.in_features)
         return y if y.dtype == x.dtype or not x.is_floating_point() else y.to(x.dtype)
 
@@ -141,7 +198,7 @@ class Linear8bitLt(_QuantLinearBase):
                 raise RuntimeError("quanta_b200 layers run on CUDA only: move the module to a GPU first")
             self.quantize_()
         xin = x if x.dtype == dt else x.to(dt)
-        y = int8_outlier_matmul(xin, self.qweight_rowwise, self.row_scale, self.threshold, self.bias)
+        y = int8_outlier_matmul(xin, self.qweight_rowwise, self.row_scale, self.threshold, self._bias_as(dt, x.device))
         return y if y.dtype == x.dtype or not x.is_floating_point() else y.to(x.dtype)
 
 
@@ -192,6 +249,6 @@ class Linear4bit(_QuantLinearBase):
                 raise RuntimeError("quanta_b200 layers run on CUDA only: move the module to a GPU first")
             self.quantize_()
         xin = x if x.dtype == self.compute_dtype else x.to(self.compute_dtype)
-        y = linear_nf4a16(xin, self.qweight, self.scale, self.bias, blocksize=self.blocksize,
+        y = linear_nf4a16(xin, self.qweight, self.scale, self._bias_as(self.compute_dtype, x.device), blocksize=self.blocksize,
                           out_features=self.out_features, in_features=self.in_features)
         return y if y.dtype == x.dtype or not x.is_floating_point() else y.to(x.dtype)

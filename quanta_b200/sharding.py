@@ -101,6 +101,16 @@ class TensorParallelLinear(nn.Module):
         self.max_rows = max_rows
         self._sym = None
 
+    def _apply(self, fn, *args, **kwargs):
+        """The kernels read scale / zero_point as float32: a ``.half()`` / ``.to(bfloat16)`` of the module must not
+        cast them (same rule as quanta_b200.nn.linear)."""
+        out = super()._apply(fn, *args, **kwargs)
+        for name in ("scale", "zero_point"):
+            buf = getattr(self, name, None)
+            if isinstance(buf, torch.Tensor) and buf.dtype != torch.float32:
+                setattr(self, name, buf.to(torch.float32))
+        return out
+
     def _symmetric_outputs(self, device):
         """Two [max_rows, out_features] output buffers in symmetric memory, mapped into every
         rank of the group.  Two, because a peer may already be writing call n+1's tiles while

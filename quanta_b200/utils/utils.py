@@ -60,7 +60,10 @@ def tensor_bits_to_bytes(tensor, bits):
 
 def _np(v):
     import numpy as np
-    return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    if isinstance(v, torch.Tensor):
+        v = v.detach().cpu()
+        return (v.float() if v.dtype in (torch.bfloat16, torch.float16) else v).numpy()
+    return np.asarray(v)
 
 
 def _with_suffix(path, suffix):
@@ -84,7 +87,13 @@ def save_quantized_tensor(q_tensor, scale, zero_point, params, file_path):
     import struct
     file_path = _with_suffix(file_path, ".qtn")
     os.makedirs(os.path.dirname(os.path.abspath(file_path)), exist_ok=True)
-    payload = [_np(q_tensor), _np(scale), _np(zero_point)]
+    import numpy as np
+    # the loader (like the reference's, utils.py:159-163) reads codes as uint8 and the parameters as float32: write
+    # exactly that, whatever the caller holds (a Python float from QuantizationState.load_state, a float16 /
+    # float64 tensor ...).  The reference writes the native dtype and then cannot read the file back.
+    payload = [np.ascontiguousarray(_np(q_tensor), dtype=np.uint8),
+               np.ascontiguousarray(_np(scale), dtype=np.float32),
+               np.ascontiguousarray(_np(zero_point), dtype=np.float32)]
     header = {"bits": params.get("bits", 8), "scheme": params.get("scheme", "symmetric"),
               "type": params.get("type", "linear"), "shape": list(q_tensor.shape),
               "dtype": str(q_tensor.dtype).replace("torch.", "", 1)}

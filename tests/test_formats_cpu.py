@@ -56,3 +56,67 @@ def test_state_reads_and_writes_the_reference_json(tmp_path):
     st.save_state(str(out))
     assert json.load(open(out)) == json.load(open(os.path.join(G, "ref_state.json")))
     assert open(out).read() == open(os.path.join(G, "ref_state.json")).read()
+
+
+def test_writer_casts_parameters_to_what_the_loader_reads(tmp_path):
+    """Python floats (what QuantizationState.load_state hands back), float64 and float16 / bfloat16
+    scales must load back as the same values — the loader always reads float32."""
+    q = torch.arange(12, dtype=torch.uint8).reshape(3, 4)
+    for k, (s, z) in enumerate([(0.05, -1.25), (torch.tensor(0.05, dtype=torch.float64), torch.tensor(-1.25, dtype=torch.float64)),
+                                (torch.tensor(0.5, dtype=torch.float16), torch.tensor(-1.25, dtype=torch.float16)),
+                                (torch.tensor(0.5, dtype=torch.bfloat16), torch.tensor(-1.25, dtype=torch.bfloat16)),
+                                (np.float64(0.05), np.float32(-1.25))]):
+        path = save_quantized_tensor(q, s, z, {"bits": 8, "scheme": "asymmetric", "type": "linear"}, str(tmp_path / f"t{k}"))
+        q2, s2, z2, _ = load_quantized_tensor(path)
+        assert torch.equal(q2, q)
+        assert abs(float(s2) - float(s)) < 1e-6 and float(z2) == -1.25
+    # per-block arrays in float64 too
+    s = torch.rand(3, dtype=torch.float64)
+    path = save_quantized_tensor(q, s, s + 1, {"bits": 8, "blocksize": 4}, str(tmp_path / "arr"))
+    _, s2, z2, _ = load_quantized_tensor(path)
+    assert s2.dtype == torch.float32 and torch.allclose(s2.double(), s, atol=1e-7) and torch.allclose(z2.double(), s + 1, atol=1e-7)
+
+
+def test_quantized_linear_state_dict_round_trip_and_casts():
+    """a quantized layer reloads through state_dict into a fresh module; module.half() keeps the
+    quantization parameters in float32 (the kernels read them as float32)."""
+    from quanta_b200.nn import Linear4bit, Linear8bitLt
+    for cls, kw in ((Linear4bit, {"quant_type": "linear"}), (Linear4bit, {}), (Linear8bitLt, {})):
+        a = cls(128, 64, **kw)
+        nbytes = 64 * 128 // 2 if a.bits == 4 else 64 * 128
+        a.qweight = torch.randint(0, 255, (nbytes,), dtype=torch.uint8)
+        a.scale = torch.rand(64 * 2)
+        a.zero_point = None if kw == {} and cls is Linear4bit else torch.rand(64 * 2)
+        a.weight = torch.nn.Parameter(torch.empty(0), requires_grad=False)
+        b = cls(128, 64, **kw)
+        res = b.load_state_dict(a.state_dict())
+        assert not res.missing_keys and not res.unexpected_keys
+        assert torch.equal(b.qweight, a.qweight) and torch.equal(b.scale, a.scale) and b.weight.numel() == 0
+        assert torch.equal(b.bias, a.bias)
+        h = b.half()
+        assert h.scale.dtype == torch.float32 and h.bias.dtype == torch.float16 and h.qweight.dtype == torch.uint8
+        if b.zero_point is not None:
+            assert h.zero_point.dtype == torch.float32
+    # a float checkpoint still loads into a fresh module
+    c, d = Linear8bitLt(32, 16), Linear8bitLt(32, 16)
+    d.load_state_dict(c.state_dict())
+    assert torch.equal(c.weight, d.weight)
+
+
+def test_gemm_wrappers_refuse_miscast_parameters():
+    """the wrappers validate dtype / size before handing raw pointers to the kernels (checked before the
+    device check would matter: these raise on any device)."""
+    import pytest
+    from quanta_b200.nn.functional import _check_weight_args
+    x = torch.zeros(2, 128, dtype=torch.float16)
+    wq = torch.zeros(64 * 128 // 2, dtype=torch.uint8)
+    s = torch.zeros(64 * 2)
+    _check_weight_args(x, wq, (("scale", s),), 64, 128, 4, 64, "t")
+    with pytest.raises(TypeError):
+        _check_weight_args(x, wq, (("scale", s.half()),), 64, 128, 4, 64, "t")
+    with pytest.raises(ValueError):
+        _check_weight_args(x, wq, (("scale", s[:-1]),), 64, 128, 4, 64, "t")
+    with pytest.raises(ValueError):
+        _check_weight_args(x, wq[:-1], (("scale", s),), 64, 128, 4, 64, "t")
+    with pytest.raises(TypeError):
+        _check_weight_args(x, wq.to(torch.int8), (("scale", s),), 64, 128, 4, 64, "t")

@@ -2,6 +2,8 @@
 
   python tools/ncu_summary.py launches <launches.csv> <out.txt>   # per-kernel count / total / share
   python tools/ncu_summary.py report   <file.ncu-rep> <out.txt>   # key metrics of each profiled launch
+  python tools/ncu_summary.py traffic  <file.ncu-rep> <out.json> [algorithmic bytes per launch] [note]
+                                                                   # DRAM bytes per launch (bench.py reads this)
 """
 import csv
 import io
@@ -68,5 +70,30 @@ def report(path, out):
     print(open(out).read())
 
 
+def traffic(path, out, algorithmic=None, note=""):
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+
+    def val(d, key):
+        v = float(d[key].replace(",", ""))
+        u = units[hdr.index(key)]
+        return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1.0)
+
+    recs = []
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        rd, wr = val(d, "dram__bytes_read.sum"), val(d, "dram__bytes_write.sum")
+        recs.append({"kernel": short(d["Kernel Name"]), "grid": d["Grid Size"], "block": d["Block Size"],
+                     "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
+                     "duration_us_under_ncu": val(d, "gpu__time_duration.sum"),
+                     "algorithmic_bytes": float(algorithmic) if algorithmic else None,
+                     "launch": note, "source": path})
+    with open(out, "w") as f:
+        json.dump(recs, f, indent=1)
+    print(open(out).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
