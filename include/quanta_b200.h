@@ -56,6 +56,7 @@ extern "C" {
 #define QUANTA_OP_BACKEND_DEQUANTIZE 2
 #define QUANTA_OP_GEMM               3
 #define QUANTA_OP_INT8_OUTLIER       4
+#define QUANTA_OP_BASE_QUANTIZE      5   /* rows, cols as passed to quanta_base_quantize */
 
 QUANTA_API int         quanta_abi_version(void);
 QUANTA_API const char* quanta_error_string(int code);
@@ -165,6 +166,25 @@ QUANTA_API int quanta_backend_quantize(const void* x, int x_dtype, int64_t rows,
 QUANTA_API int quanta_backend_dequantize(const uint8_t* q, int64_t rows, int64_t cols, int64_t nchan, int bits,
                               const float* scale, const float* zp, float* out,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- convention C: Quanta/functional/base.py (BaseQuantizer, row N4) -------
+ *
+ * Replaces BaseQuantizer(num_bits, symmetric).quantize(tensor, per_channel)
+ * (base.py:11-59): symmetric as convention B (scale = rcp(absmax)*Q, zp = 0,
+ * codes offset by 2^(bits-1)); asymmetric scale = rcp(mx-mn)*L, zp = mn (a
+ * float offset), q = clamp(round((x - zp)*scale), 0, L).  If allclose(min, max)
+ * holds for ALL channels, scale = 1 and zp = min and the codes are still computed
+ * with them (base.py:26-27).  bits = 8 or 4; per_channel reduces over dim 0 of
+ * the [rows, cols] tensor; scale_out / zp_out: 1 or cols values.
+ * quanta_base_dequantize replaces .dequantize (base.py:61-72): symmetric
+ * (int8(q) - 2^(bits-1)) / scale, else q / scale + zp (true divides); the
+ * branch is the quantizer's `symmetric`, not inferred from zp.                 */
+QUANTA_API int quanta_base_quantize(const void* x, int x_dtype, int64_t rows, int64_t cols,
+                         int per_channel, int symmetric, int bits,
+                         uint8_t* q_out, float* scale_out, float* zp_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+QUANTA_API int quanta_base_dequantize(const uint8_t* q, int64_t rows, int64_t cols, int64_t nchan, int bits,
+                           int symmetric, const float* scale, const float* zp, float* out, void* stream);
 
 /* ---- the rest of the quant_type switch (row N4): nf8, fp4, fp8 ---------------
  *

@@ -238,6 +238,63 @@ def backend_dequantize(q, scale, zp, bits=8):
 
 
 # --------------------------------------------------------------------------
+# Convention C — Quanta/functional/base.py (BaseQuantizer), SURVEY Appendix A.3
+# --------------------------------------------------------------------------
+
+def base_quantize(x, bits=8, per_channel=False, symmetric=True):
+    """Row N4 (BaseQuantizer.quantize, base.py:11-59).  Like convention B in the symmetric case
+    (``scale = max_val / abs_max`` = reciprocal * int, codes offset by 2^(bits-1)); asymmetric:
+    ``scale = (2^bits - 1) / (max - min)``, ``zero_point = min`` (not rounded),
+    ``q = clamp(round((x - zero_point) * scale), 0, 2^bits - 1)``.  If ``allclose(min, max)`` holds for ALL
+    channels the parameters become ``(ones_like(min), min)`` and the codes are STILL computed with them
+    (base.py:26-27, :43-57) — unlike convention B, which returns zero codes."""
+    with np.errstate(all="ignore"):
+        x = _f32(x)
+        Q = F32(2 ** (bits - 1) - 1)
+        L = F32(2 ** bits - 1)
+        OFF = 2 ** (bits - 1)
+        if per_channel:
+            if x.ndim < 2:
+                raise ValueError("per_channel needs a tensor with dim() > 1")   # tensor.min(dim=None, keepdim=True) raises
+            mn, mx = _min_max(x, axis=0, keepdims=True)
+        else:
+            mn, mx = _min_max(x)
+            mn, mx = np.asarray(mn), np.asarray(mx)
+        if bool(np.all(_isclose(mn, mx))):                                     # :26-27
+            scale, zp = np.ones_like(mn), mn
+        elif symmetric:                                                        # :29-32
+            am = np.maximum(np.abs(mn), np.abs(mx))
+            am = np.where(np.isnan(mn) | np.isnan(mx), F32(np.nan), am).astype(np.float32)
+            scale = ((F32(1) / am).astype(np.float32) * Q).astype(np.float32)
+            zp = np.zeros_like(mn)
+        else:                                                                  # :33-35
+            rng = (mx - mn).astype(np.float32)
+            scale = ((F32(1) / rng).astype(np.float32) * L).astype(np.float32)
+            zp = mn
+        if symmetric:                                                          # :44-49
+            v = np.clip(np.rint((x * scale).astype(np.float32)), -Q, Q)
+            v = np.where(np.isnan(v), F32(0), v)
+            q = (v.astype(np.int32) + OFF).astype(np.uint8)
+        else:                                                                  # :50-54
+            v = ((x - zp).astype(np.float32) * scale).astype(np.float32)
+            q = _to_u8(np.clip(np.rint(v), F32(0), L))
+        return q, np.asarray(scale, np.float32), np.asarray(zp, np.float32)
+
+
+def base_dequantize(q, scale, zp, bits=8, symmetric=True):
+    """BaseQuantizer.dequantize (base.py:61-72): symmetric ``(int8(q) - 2^(bits-1)).float() / scale`` (int8
+    arithmetic, wraps), else ``q.float() / scale + zero_point`` — true divides; which branch runs is decided by
+    the quantizer's ``symmetric`` attribute, not by the zero-point values."""
+    with np.errstate(all="ignore"):
+        q = np.asarray(q, np.uint8)
+        scale, zp = _f32(scale), _f32(zp)
+        if symmetric:
+            qi = (q.astype(np.int8).astype(np.int32) - 2 ** (bits - 1)).astype(np.int8).astype(np.float32)
+            return (qi / scale).astype(np.float32)
+        return ((q.astype(np.float32) / scale).astype(np.float32) + zp).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
 # G1 / G2 — composition oracle for the quantized Linear layers
 # --------------------------------------------------------------------------
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libquanta_b200.so")
 
 MODE_TENSOR, MODE_DIM0, MODE_BLOCK = 0, 1, 2
 F32, F16, BF16 = 0, 1, 2
-OP_QUANTIZE_AFFINE, OP_BACKEND_QUANTIZE, OP_BACKEND_DEQUANTIZE, OP_GEMM, OP_INT8_OUTLIER = range(5)
+OP_QUANTIZE_AFFINE, OP_BACKEND_QUANTIZE, OP_BACKEND_DEQUANTIZE, OP_GEMM, OP_INT8_OUTLIER, OP_BASE_QUANTIZE = range(6)
 
 # every symbol include/quanta_b200.h declares: name -> (restype, argtypes)
 _i64, _int, _vp, _sz, _f = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_float
@@ -34,6 +34,8 @@ SIGNATURES = {
     "quanta_unpack4": (_int, [_vp, _i64, _vp, _vp]),
     "quanta_backend_quantize": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_backend_dequantize": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "quanta_base_quantize": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "quanta_base_dequantize": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp]),
     "quanta_nf8_levels": (_int, [_vp]),
     "quanta_quantize_nf8": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp]),
     "quanta_dequantize_nf8": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp]),

@@ -5,6 +5,7 @@ namespace quanta {
 size_t quantize_workspace_bytes(int64_t cols);
 size_t gemm_workspace_bytes(int64_t M, int64_t N);
 size_t int8_outlier_workspace_bytes(int64_t M, int64_t N);
+size_t base_workspace_bytes(int64_t groups);
 }  // namespace quanta
 
 extern "C" int quanta_abi_version(void) { return QUANTA_B200_ABI_VERSION; }
@@ -28,6 +29,7 @@ extern "C" size_t quanta_workspace_bytes(int op, int64_t rows, int64_t cols) {
         case QUANTA_OP_BACKEND_DEQUANTIZE: return 256;
         case QUANTA_OP_GEMM: return quanta::gemm_workspace_bytes(rows, cols);
         case QUANTA_OP_INT8_OUTLIER: return quanta::int8_outlier_workspace_bytes(rows, cols);
+        case QUANTA_OP_BASE_QUANTIZE: return quanta::base_workspace_bytes(cols);
     }
     return 256;
 }

@@ -99,3 +99,68 @@ def test_grid_barrier_timeout_raises_and_recovers(Q):
     qo, so, zo = O.quantize_affine(x.numpy(), 8, O.MODE_TENSOR)
     assert np.array_equal(q2.cpu().numpy(), qo) and torch.equal(q2, q0)
     assert float(s2) == float(so) and float(z2) == float(zo)
+
+
+# ---- guard bands: compute-sanitizer is closed on this pool (profiles/r02_sanitizer.txt), so out-of-bounds WRITES are
+# ---- looked for with our own canaries: every output lives inside a larger sentinel-filled buffer, odd sizes included
+def _guarded(nbytes, dtype=torch.uint8, pad=4096):
+    raw = torch.full((nbytes + 2 * pad,), 0xA5, dtype=torch.uint8, device="cuda")
+    return raw, raw[pad:pad + nbytes], pad
+
+
+def _intact(raw, nbytes, pad):
+    return bool((raw[:pad] == 0xA5).all()) and bool((raw[pad + nbytes:] == 0xA5).all())
+
+
+@pytest.mark.parametrize("n_rows,n_cols", [(520, 1024), (257, 4160), (33, 192), (1, 64)])
+def test_quantize_entries_stay_inside_their_outputs(Q, n_rows, n_cols):
+    from quanta_b200 import _lib, _host
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    x = torch.randn(n_rows, n_cols, device=dev)
+    n = n_rows * n_cols
+    st = _host.stream_ptr(dev)
+    for mode, block, bits, pack in ((_lib.MODE_BLOCK, 64, 4, 1), (_lib.MODE_BLOCK, 64, 4, 0), (_lib.MODE_BLOCK, 64, 8, 0),
+                                    (_lib.MODE_TENSOR, 0, 8, 0), (_lib.MODE_TENSOR, 0, 4, 0), (_lib.MODE_DIM0, 0, 8, 0)):
+        rows, cols = (n_rows, n_cols) if mode == _lib.MODE_DIM0 else (1, n)
+        nparam = n // 64 if mode == _lib.MODE_BLOCK else (n_cols if mode == _lib.MODE_DIM0 else 1)
+        qbytes = (n + 1) // 2 if pack else n
+        rq, q, pad = _guarded(qbytes)
+        rs, s, _ = _guarded(nparam * 4)
+        rz, z, _ = _guarded(nparam * 4)
+        ws = _host.quantize_workspace(dev, L.quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, rows if mode == _lib.MODE_DIM0 else 1,
+                                                                    cols if mode == _lib.MODE_DIM0 else 1))
+        rc = L.quanta_quantize_affine(x.data_ptr(), _lib.F32, rows, cols, mode, block, bits, pack, q.data_ptr(), s.data_ptr(),
+                                      z.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        assert rc == 0, (mode, bits, pack, rc)
+        torch.cuda.synchronize()
+        assert _intact(rq, qbytes, pad) and _intact(rs, nparam * 4, pad) and _intact(rz, nparam * 4, pad), (mode, bits, pack)
+        # and back: dequantize into a guarded fp32 buffer
+        ro, o, _ = _guarded(n * 4)
+        rc = L.quanta_dequantize_affine(q.data_ptr(), pack, rows, cols, mode, block, s.data_ptr(), z.data_ptr(), o.data_ptr(), _lib.F32, st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert _intact(ro, n * 4, pad)
+        d = o.view(torch.float32).reshape(n_rows, n_cols)
+        assert float((d - x).abs().max()) <= float(s.view(torch.float32).max()) * 0.51 + 1e-6
+
+
+@pytest.mark.parametrize("case", [(200, 512, 7, 4), (136, 1536, 16, 4), (200, 320, 33, 8), (384, 1024, 130, 4), (128, 256, 1, 8)])
+def test_gemm_stays_inside_y(Q, case):
+    from quanta_b200 import _lib, _host
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    N, K, M, bits = case
+    w = torch.randn(N, K, device=dev) * 0.02
+    x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    qf = Q.quantize_4bit(w, blocksize=64, packed=True) if bits == 4 else Q.quantize_8bit(w, blocksize=64)
+    ry, y, pad = _guarded(M * N * 2)
+    ws = _host.gemm_workspace(dev, L.quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+    rc = L.quanta_gemm_wna16(x.data_ptr(), _lib.BF16, qf[0].data_ptr(), bits, qf[1].data_ptr(), qf[2].data_ptr(), 64, None,
+                             y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert _intact(ry, M * N * 2, pad)
+    from quanta_b200.nn import linear_wna16
+    assert torch.equal(y.view(torch.bfloat16).reshape(M, N), linear_wna16(x, *qf, None, bits=bits, blocksize=64, out_features=N))
+    assert int(ws[:65536].view(torch.int32).abs().sum()) == 0            # counters left zero
