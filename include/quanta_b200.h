@@ -144,6 +144,11 @@ QUANTA_API int quanta_dequantize_nf4(const uint8_t* q, int packed4, int64_t n, i
  * unpack: out[2i] = b & 0xF, out[2i+1] = b >> 4; out holds 2*nbytes codes. */
 QUANTA_API int quanta_pack4(const uint8_t* q, int64_t n, uint8_t* packed, void* stream);
 QUANTA_API int quanta_unpack4(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream);
+/* The opposite nibble order of ModelQuantize._pack_tensor / _unpack_tensor
+ * (Quanta/functional/model.py:73-94): packed[i] = (q[2i] << 4) | q[2i+1] — the
+ * first element goes to the HIGH nibble; one zero pad if n is odd.             */
+QUANTA_API int quanta_pack4_hi(const uint8_t* q, int64_t n, uint8_t* packed, void* stream);
+QUANTA_API int quanta_unpack4_hi(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream);
 
 /* ---- convention B: Quanta/backends/cpu/quantization.py -------------------
  *

@@ -32,6 +32,8 @@ SIGNATURES = {
     "quanta_dequantize_nf4": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _int, _vp]),
     "quanta_pack4": (_int, [_vp, _i64, _vp, _vp]),
     "quanta_unpack4": (_int, [_vp, _i64, _vp, _vp]),
+    "quanta_pack4_hi": (_int, [_vp, _i64, _vp, _vp]),
+    "quanta_unpack4_hi": (_int, [_vp, _i64, _vp, _vp]),
     "quanta_backend_quantize": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_backend_dequantize": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_base_quantize": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -8,19 +8,24 @@ namespace quanta {
 // [b0 b1 b2 b3] -> byte0 = b0 | (b1 << 4), byte2 = b2 | (b3 << 4) in uint8
 // arithmetic: the high nibble of b1/b3 drops, b0/b2 are NOT masked (reference
 // behaviour for inputs > 15, utils.py:34).
+// HI = false: utils.py order (even index -> low nibble).  HI = true: ModelQuantize._pack_tensor's order
+// (Quanta/functional/model.py:73-82: byte = (t[2i] << 4) | t[2i+1], first element -> HIGH nibble).
+template <bool HI>
 __device__ __forceinline__ uint32_t pack_word(uint32_t w) {
-    return (w & 0x00FF00FFu) | ((w >> 4) & 0x00F000F0u);
+    return HI ? (((w << 4) & 0x00F000F0u) | ((w >> 8) & 0x00FF00FFu))
+              : ((w & 0x00FF00FFu) | ((w >> 4) & 0x00F000F0u));
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r;
 }
 
 // 16 codes (uint4) -> 8 bytes (uint2) per vector.
+template <bool HI>
 __global__ void __launch_bounds__(256) pack4_vec_kernel(const uint4* __restrict__ q, int64_t nvec, uint2* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto pack = [](uint4 v) {
-        uint32_t a = pack_word(v.x), b = pack_word(v.y), c = pack_word(v.z), d = pack_word(v.w);
+        uint32_t a = pack_word<HI>(v.x), b = pack_word<HI>(v.y), c = pack_word<HI>(v.z), d = pack_word<HI>(v.w);
         return make_uint2(prmt(a, b, 0x6420u), prmt(c, d, 0x6420u));
     };
     for (; i + 3 * stride < nvec; i += 4 * stride) {
@@ -33,22 +38,25 @@ __global__ void __launch_bounds__(256) pack4_vec_kernel(const uint4* __restrict_
     for (; i < nvec; i += stride) __stcs(out + i, pack(__ldcs(q + i)));
 }
 
+template <bool HI>
 __global__ void __launch_bounds__(256) pack4_tail_kernel(const uint8_t* __restrict__ q, int64_t start, int64_t n,
                                                          uint8_t* __restrict__ out) {
     const int64_t i = start + 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
     uint8_t lo = q[i];
     uint8_t hi = (i + 1 < n) ? q[i + 1] : 0;                 // one zero pad if n is odd (utils.py:31-32)
-    out[i >> 1] = (uint8_t)(lo | (uint8_t)(hi << 4));
+    out[i >> 1] = HI ? (uint8_t)((uint8_t)(lo << 4) | hi) : (uint8_t)(lo | (uint8_t)(hi << 4));
 }
 
 // 8 packed bytes (uint2) -> 16 codes (uint4) per vector.
+template <bool HI>
 __global__ void __launch_bounds__(256) unpack4_vec_kernel(const uint2* __restrict__ p, int64_t nvec, uint4* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto unpack = [](uint2 v) {
-        uint32_t lo0 = v.x & 0x0F0F0F0Fu, hi0 = (v.x >> 4) & 0x0F0F0F0Fu;
-        uint32_t lo1 = v.y & 0x0F0F0F0Fu, hi1 = (v.y >> 4) & 0x0F0F0F0Fu;
+        // lo* = the nibble that decodes to the even output index
+        uint32_t lo0 = (HI ? v.x >> 4 : v.x) & 0x0F0F0F0Fu, hi0 = (HI ? v.x : v.x >> 4) & 0x0F0F0F0Fu;
+        uint32_t lo1 = (HI ? v.y >> 4 : v.y) & 0x0F0F0F0Fu, hi1 = (HI ? v.y : v.y >> 4) & 0x0F0F0F0Fu;
         return make_uint4(prmt(lo0, hi0, 0x5140u), prmt(lo0, hi0, 0x7362u), prmt(lo1, hi1, 0x5140u), prmt(lo1, hi1, 0x7362u));
     };
     for (; i + 3 * stride < nvec; i += 4 * stride) {
@@ -61,13 +69,14 @@ __global__ void __launch_bounds__(256) unpack4_vec_kernel(const uint2* __restric
     for (; i < nvec; i += stride) __stcs(out + i, unpack(__ldcs(p + i)));
 }
 
+template <bool HI>
 __global__ void __launch_bounds__(256) unpack4_tail_kernel(const uint8_t* __restrict__ p, int64_t start, int64_t nbytes,
                                                            uint8_t* __restrict__ out) {
     const int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbytes) return;
     uint8_t b = p[i];
-    out[2 * i] = b & 0x0F;
-    out[2 * i + 1] = (b >> 4) & 0x0F;
+    out[2 * i] = HI ? (b >> 4) & 0x0F : b & 0x0F;
+    out[2 * i + 1] = HI ? b & 0x0F : (b >> 4) & 0x0F;
 }
 
 static unsigned grid_for(int64_t nvec) {
@@ -80,34 +89,41 @@ static unsigned grid_for(int64_t nvec) {
 
 using namespace quanta;
 
-extern "C" int quanta_pack4(const uint8_t* q, int64_t n, uint8_t* packed, void* stream) {
+template <bool HI>
+static int pack4_launch(const uint8_t* q, int64_t n, uint8_t* packed, void* stream) {
     if (!q || !packed || n < 0) return QUANTA_EINVAL;
     if (n == 0) return QUANTA_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ok = (reinterpret_cast<uintptr_t>(q) % 16 == 0) && (reinterpret_cast<uintptr_t>(packed) % 8 == 0);
     const int64_t nvec = ok ? n / 16 : 0;
     if (nvec > 0)
-        pack4_vec_kernel<<<grid_for(nvec), 256, 0, st>>>(reinterpret_cast<const uint4*>(q), nvec,
-                                                        reinterpret_cast<uint2*>(packed));
+        pack4_vec_kernel<HI><<<grid_for(nvec), 256, 0, st>>>(reinterpret_cast<const uint4*>(q), nvec,
+                                                            reinterpret_cast<uint2*>(packed));
     const int64_t start = nvec * 16;
     if (start < n) {
         const int64_t pairs = (n - start + 1) / 2;
-        pack4_tail_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(q, start, n, packed);
+        pack4_tail_kernel<HI><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(q, start, n, packed);
     }
     return cuda_status(cudaGetLastError());
 }
 
-extern "C" int quanta_unpack4(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream) {
+template <bool HI>
+static int unpack4_launch(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream) {
     if (!packed || !out || nbytes < 0) return QUANTA_EINVAL;
     if (nbytes == 0) return QUANTA_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ok = (reinterpret_cast<uintptr_t>(packed) % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
     const int64_t nvec = ok ? nbytes / 8 : 0;
     if (nvec > 0)
-        unpack4_vec_kernel<<<grid_for(nvec), 256, 0, st>>>(reinterpret_cast<const uint2*>(packed), nvec,
-                                                          reinterpret_cast<uint4*>(out));
+        unpack4_vec_kernel<HI><<<grid_for(nvec), 256, 0, st>>>(reinterpret_cast<const uint2*>(packed), nvec,
+                                                              reinterpret_cast<uint4*>(out));
     const int64_t start = nvec * 8;
     if (start < nbytes)
-        unpack4_tail_kernel<<<(unsigned)((nbytes - start + 255) / 256), 256, 0, st>>>(packed, start, nbytes, out);
+        unpack4_tail_kernel<HI><<<(unsigned)((nbytes - start + 255) / 256), 256, 0, st>>>(packed, start, nbytes, out);
     return cuda_status(cudaGetLastError());
 }
+
+extern "C" int quanta_pack4(const uint8_t* q, int64_t n, uint8_t* packed, void* stream) { return pack4_launch<false>(q, n, packed, stream); }
+extern "C" int quanta_unpack4(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream) { return unpack4_launch<false>(packed, nbytes, out, stream); }
+extern "C" int quanta_pack4_hi(const uint8_t* q, int64_t n, uint8_t* packed, void* stream) { return pack4_launch<true>(q, n, packed, stream); }
+extern "C" int quanta_unpack4_hi(const uint8_t* packed, int64_t nbytes, uint8_t* out, void* stream) { return unpack4_launch<true>(packed, nbytes, out, stream); }
