@@ -211,6 +211,16 @@ QUANTA_API int quanta_quantize_fp(const void* x, int x_dtype, int64_t n, int bit
 QUANTA_API int quanta_dequantize_fp(const uint8_t* q, int64_t n, int bits, int bias,
                          void* out, int out_dtype, void* stream);
 
+/* ---- convert_precision for per-tensor linear codes (row N3) ------------------
+ * Replaces convert_precision(q, {type "linear", scalar scale / zero_point}, target_bits, "linear")
+ * (utils/utils.py:216-279), i.e. dequantize_*bit + quantize_*bit per tensor, bit for bit, in two
+ * passes over the CODES (3 B/element instead of 14): q holds n codes (one per byte, any source bit
+ * depth), src_scale / src_zp are DEVICE pointers to one float each; q_out n codes, scale_out /
+ * zp_out one float each.  workspace >= 256 bytes of scratch.                   */
+QUANTA_API int quanta_convert_linear(const uint8_t* q, int64_t n, const float* src_scale, const float* src_zp,
+                          int target_bits, uint8_t* q_out, float* scale_out, float* zp_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- dequantize-then-matmul behind Quanta/nn/linear.py -------------------
  *
  * Replaces the placeholder F.linear in Linear4bit.forward (nn/linear.py:81-83)

@@ -38,6 +38,7 @@ SIGNATURES = {
     "quanta_backend_dequantize": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_base_quantize": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_base_dequantize": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp]),
+    "quanta_convert_linear": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_nf8_levels": (_int, [_vp]),
     "quanta_quantize_nf8": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp]),
     "quanta_dequantize_nf8": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp]),

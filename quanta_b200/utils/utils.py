@@ -161,12 +161,50 @@ def convert_precision(q_tensor, source_params, target_bits, target_type="linear"
         raise ValueError(f"Unsupported source bit depth: {source_bits}")
     if target_bits not in encode:
         raise ValueError(f"Unsupported target bit depth: {target_bits}")
-    full = decode[source_bits](q_tensor, source_params.get("scale"), source_params.get("zero_point"),
-                               quant_type=source_params.get("type", "linear"))
-    q, first, second = encode[target_bits](full, quant_type=target_type)
+    fused = _convert_linear_fused(q_tensor, source_params, target_bits, target_type)
+    if fused is not None:
+        q, first, second = fused
+    else:
+        full = decode[source_bits](q_tensor, source_params.get("scale"), source_params.get("zero_point"),
+                                   quant_type=source_params.get("type", "linear"))
+        q, first, second = encode[target_bits](full, quant_type=target_type)
     scheme = target_scheme if target_scheme is not None else source_params.get("scheme", "symmetric")
     return q, first, second, {"bits": target_bits, "type": target_type, "scheme": scheme, "scale": first,
                               "zero_point": second, "shape": tuple(q.shape)}
+
+
+def _convert_linear_fused(q_tensor, source_params, target_bits, target_type):
+    """linear -> linear with ONE (scale, zero_point) for the tensor: the new code is a function of the old code, so
+    the conversion is a 256-entry table applied to the codes (``quanta_convert_linear``: 3 B/element instead of a
+    dequantize + quantize through fp32).  Returns None when the case does not apply (other types, per-channel /
+    blockwise parameters)."""
+    from .. import _host, _lib
+    if source_params.get("type", "linear") != "linear" or target_type != "linear":
+        return None
+    if not (isinstance(q_tensor, torch.Tensor) and q_tensor.is_cuda and q_tensor.dtype == torch.uint8 and q_tensor.numel() > 0):
+        return None
+    dev = q_tensor.device
+    params = []
+    for key in ("scale", "zero_point"):
+        v = source_params.get(key)
+        if v is None:
+            return None
+        v = torch.as_tensor(v, dtype=torch.float32, device=dev)
+        if v.numel() != 1:
+            return None
+        params.append(v.reshape(1).contiguous())
+    q = q_tensor.detach()
+    if not q.is_contiguous():
+        q = q.contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty(q.shape, dtype=torch.uint8, device=dev)
+        scale, zp = torch.empty((), dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev)
+        ws = _host.workspace(dev, 256)
+        st = _lib.lib().quanta_convert_linear(q.data_ptr(), q.numel(), params[0].data_ptr(), params[1].data_ptr(), int(target_bits),
+                                              out.data_ptr(), scale.data_ptr(), zp.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _host.stream_ptr(dev))
+    _lib.check(st, "quanta_convert_linear")
+    return out, scale, zp
 
 
 def convert_8bit_to_4bit(q_tensor, source_params, target_type="linear"):

@@ -52,3 +52,25 @@ def test_state_round_trip_on_cuda(tmp_path):
     assert torch.equal(d, Q.dequantize_8bit(q, s, z))
     q4 = st2.convert_tensor_precision("w", 4)
     assert np.array_equal(q4.cpu().numpy(), Z["c84_linear/q"]) and st2.get_tensor_params("w")["bits"] == 4
+
+
+@pytest.mark.parametrize("n", [1, 17, 4096, 1000003])
+@pytest.mark.parametrize("src_bits,tgt_bits", [(8, 4), (4, 8), (8, 8), (4, 4)])
+def test_fused_convert_equals_dequantize_plus_quantize(n, src_bits, tgt_bits):
+    """quanta_convert_linear (a code -> code table, 3 B/element) against the two-step path it replaces, bit for bit,
+    incl. sparse code sets (min / max over the codes that occur), negative and non-finite scales."""
+    import quanta_b200 as Q
+    from quanta_b200.utils import convert_precision
+    g = torch.Generator().manual_seed(n + src_bits)
+    top = 256 if src_bits == 8 else 16
+    for trial, (s, z) in enumerate([(0.0123, -1.5), (3.7e-5, 0.25), (-0.5, 2.0), (float("inf"), 0.0), (0.0, 7.0), (1e30, -1e30)]):
+        q = torch.randint(3 if trial % 2 else 0, top - (5 if trial % 2 else 0), (n,), dtype=torch.uint8, generator=g).cuda()
+        params = {"bits": src_bits, "type": "linear", "scheme": "asymmetric", "scale": torch.tensor(s), "zero_point": torch.tensor(z)}
+        nq, ns, nz, newp = convert_precision(q, params, tgt_bits, "linear")
+        deq = (Q.dequantize_8bit if src_bits == 8 else Q.dequantize_4bit)(q, torch.tensor(s).cuda(), torch.tensor(z).cuda())
+        rq, rs, rz = (Q.quantize_8bit if tgt_bits == 8 else Q.quantize_4bit)(deq)
+        assert torch.equal(nq, rq), (trial, s, z)
+        for a, b in ((ns, rs), (nz, rz)):
+            a, b = a.reshape(()).cpu(), b.reshape(()).cpu()
+            assert (torch.isnan(a) and torch.isnan(b)) or a.view(torch.int32) == b.view(torch.int32), (trial, s, z)
+        assert newp["bits"] == tgt_bits and newp["shape"] == tuple(q.shape)
