@@ -38,11 +38,11 @@ def _quantize(tensor, per_channel, symmetric, bits):
     else:
         rows, cols, pshape = 1, x.numel(), ()
     nparam = cols if per_channel else 1
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         q = torch.empty(x.shape, dtype=torch.uint8, device=dev)
         scale = torch.empty(nparam, dtype=torch.float32, device=dev)
         zp = torch.empty(nparam, dtype=torch.float32, device=dev)
-        ws = _host.quantize_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_BACKEND_QUANTIZE, rows if per_channel else 1,
+        ws = _host.quantize_workspace(dev, _host.workspace_bytes(_lib.OP_BACKEND_QUANTIZE, rows if per_channel else 1,
                                                                     cols if per_channel else 1))
         st = _lib.lib().quanta_backend_quantize(x.data_ptr(), code, rows, cols, int(bool(per_channel)),
                                                 int(bool(symmetric)), bits, q.data_ptr(), scale.data_ptr(),
@@ -73,7 +73,7 @@ def _dequantize(q_tensor, scale, zero_point, bits):
     rows, cols = _host.rows_cols(q) if nchan > 1 else (1, n)
     if nchan not in (1, cols):
         raise ValueError(f"scale of {nchan} elements does not broadcast over codes of shape {tuple(q.shape)}")
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         ws = _host.workspace(dev, 256)
         st = _lib.lib().quanta_backend_dequantize(q.data_ptr(), rows, cols, nchan, bits, scale.data_ptr(),
                                                   zp.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),

@@ -44,11 +44,11 @@ class BaseQuantizer:
             rows, cols, pshape = 1, x.numel(), ()
         nparam = cols if per_channel else 1
         L = _lib.lib()
-        with torch.cuda.device(dev):
+        with _host.device_guard(dev):
             q = torch.empty(x.shape, dtype=torch.uint8, device=dev)
             scale = torch.empty(nparam, dtype=torch.float32, device=dev)
             zp = torch.empty(nparam, dtype=torch.float32, device=dev)
-            ws = _host.workspace(dev, L.quanta_workspace_bytes(_lib.OP_BASE_QUANTIZE, rows, cols))
+            ws = _host.workspace(dev, _host.workspace_bytes(_lib.OP_BASE_QUANTIZE, rows, cols))
             st = L.quanta_base_quantize(x.data_ptr(), code, rows, cols, int(bool(per_channel)), int(bool(self.symmetric)),
                                         self.num_bits, q.data_ptr(), scale.data_ptr(), zp.data_ptr(), ws.data_ptr(),
                                         ws.numel(), _host.stream_ptr(dev))
@@ -80,7 +80,7 @@ class BaseQuantizer:
                                  "reference's per_channel results ([1, *shape[1:]])")
         else:
             rows, cols = 1, q.numel()
-        with torch.cuda.device(dev):
+        with _host.device_guard(dev):
             st = _lib.lib().quanta_base_dequantize(q.data_ptr(), rows, cols, nchan, self.num_bits, int(bool(self.symmetric)),
                                                    scale.data_ptr(), zp.data_ptr(), out.data_ptr(), _host.stream_ptr(dev))
         _lib.check(st, "quanta_base_dequantize")

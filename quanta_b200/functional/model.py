@@ -82,7 +82,7 @@ class ModelQuantize:
         q = q.contiguous()
         out = torch.empty((q.numel() + 1) // 2, dtype=torch.uint8, device=q.device)
         if q.numel():
-            with torch.cuda.device(q.device):
+            with _host.device_guard(q.device):
                 st = _lib.lib().quanta_pack4_hi(q.data_ptr(), q.numel(), out.data_ptr(), _host.stream_ptr(q.device))
             _lib.check(st, "quanta_pack4_hi")
         return out
@@ -99,7 +99,7 @@ class ModelQuantize:
             raise ValueError(f"packed codes hold {p.numel()} bytes, shape {tuple(original_shape)} needs {(n + 1) // 2}")
         out = torch.empty(p.numel() * 2, dtype=torch.uint8, device=p.device)
         if p.numel():
-            with torch.cuda.device(p.device):
+            with _host.device_guard(p.device):
                 st = _lib.lib().quanta_unpack4_hi(p.data_ptr(), p.numel(), out.data_ptr(), _host.stream_ptr(p.device))
             _lib.check(st, "quanta_unpack4_hi")
         return out[:n].reshape(tuple(original_shape))

@@ -49,12 +49,12 @@ def _quantize_linear(tensor, bits, per_channel, blocksize, packed):
         mode, nparam, pshape, B = _lib.MODE_DIM0, cols, (1,) + tuple(x.shape[1:]), 0
     else:
         mode, rows, cols, nparam, pshape, B = _lib.MODE_TENSOR, 1, n, 1, (), 0
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         scale = torch.empty(nparam, dtype=torch.float32, device=dev)
         zp = torch.empty(nparam, dtype=torch.float32, device=dev)
         q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
         # only the two-pass modes need scratch: per-tensor partials, or per-column partials for dim 0
-        ws_bytes = _lib.lib().quanta_workspace_bytes(_lib.OP_QUANTIZE_AFFINE, rows if mode == _lib.MODE_DIM0 else 1,
+        ws_bytes = _host.workspace_bytes(_lib.OP_QUANTIZE_AFFINE, rows if mode == _lib.MODE_DIM0 else 1,
                                                      cols if mode == _lib.MODE_DIM0 else 1)
         ws = _host.quantize_workspace(dev, ws_bytes)
         st = _lib.lib().quanta_quantize_affine(x.data_ptr(), code, rows, cols, mode, B, bits, int(bool(packed)),
@@ -103,7 +103,7 @@ def _quantize_nf4(tensor, blocksize, packed):
         raise ValueError(f"numel ({n}) must be a multiple of blocksize ({blocksize})")
     if B and (B < 16 or B > 512 or (B & (B - 1))):
         raise ValueError(f"NF4 blocksize must be 16 * 2^j <= 512 (got {blocksize}); the affine formats take any block size")
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
         absmax = torch.empty(n // B if B else 1, dtype=torch.float32, device=dev)
         st = _lib.lib().quanta_quantize_nf4(x.data_ptr(), code, n, B, int(bool(packed)), q.data_ptr(),
@@ -135,7 +135,7 @@ def _dequantize_nf4(q_tensor, absmax, blocksize, packed, shape, out_dtype):
         raise ValueError(f"NF4 blocksize must be 16 * 2^j <= 512 (got {blocksize}); the affine formats take any block size")
     if (B and absmax.numel() != n // B) or (not B and absmax.numel() != 1):
         raise ValueError("absmax does not match blocksize")
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         st = _lib.lib().quanta_dequantize_nf4(q.data_ptr(), int(bool(packed)), n, B, absmax.data_ptr(), out.data_ptr(),
                                               _host._DTYPE[out_dtype], _host.stream_ptr(dev))
     _lib.check(st, "quanta_dequantize_nf4")
@@ -169,7 +169,7 @@ def _quantize_nf8(tensor, blocksize):
     B = 0 if blocksize is None else int(blocksize)
     if B and n % B:
         raise ValueError(f"numel ({n}) must be a multiple of blocksize ({blocksize})")
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         q = torch.empty(n, dtype=torch.uint8, device=dev)
         absmax = torch.empty(n // B if B else 1, dtype=torch.float32, device=dev)
         st = _lib.lib().quanta_quantize_nf8(x.data_ptr(), code, n, B, q.data_ptr(), absmax.data_ptr(), _host.stream_ptr(dev))
@@ -193,7 +193,7 @@ def _dequantize_nf8(q_tensor, absmax, blocksize, out_dtype):
     B = 0 if blocksize is None else int(blocksize)
     if (B and absmax.numel() != n // B) or (not B and absmax.numel() != 1):
         raise ValueError("absmax does not match blocksize")
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         st = _lib.lib().quanta_dequantize_nf8(q.data_ptr(), n, B, absmax.data_ptr(), out.data_ptr(),
                                               _host._DTYPE[out_dtype], _host.stream_ptr(dev))
     _lib.check(st, "quanta_dequantize_nf8")
@@ -205,7 +205,7 @@ def _quantize_fp(tensor, bits):
     x, code, n, dev = _prep_input(tensor)
     q = torch.empty(tensor.shape, dtype=torch.uint8, device=dev)
     if n:
-        with torch.cuda.device(dev):
+        with _host.device_guard(dev):
             st = _lib.lib().quanta_quantize_fp(x.data_ptr(), code, n, bits, q.data_ptr(), _host.stream_ptr(dev))
         _lib.check(st, "quanta_quantize_fp")
     return q, None, (1 if bits == 4 else 7)
@@ -223,7 +223,7 @@ def _dequantize_fp(q_tensor, bias, bits, out_dtype):
         raise ValueError("the exponent bias must be an integer")
     out = torch.empty(q.shape, dtype=out_dtype, device=dev)
     if q.numel():
-        with torch.cuda.device(dev):
+        with _host.device_guard(dev):
             st = _lib.lib().quanta_dequantize_fp(q.data_ptr(), q.numel(), bits, int(bias), out.data_ptr(),
                                                  _host._DTYPE[out_dtype], _host.stream_ptr(dev))
         _lib.check(st, "quanta_dequantize_fp")
@@ -276,7 +276,7 @@ def _quantize_many(tensors, bits, blocksize, packed):
             raise ValueError(f"numel ({n}) must be a positive multiple of blocksize ({blocksize})")
         xs.append(x)
     code = _host.dtype_code(xs[0])
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         for x in xs:
             n = x.numel()
             q = torch.empty((n + 1) // 2 if packed else n, dtype=torch.uint8, device=dev)
@@ -357,7 +357,7 @@ def _dequantize_linear(q_tensor, scale, zero_point, blocksize, packed, shape, ou
         raise ValueError(f"scale of shape {tuple(scale.shape)} does not broadcast like the reference's per-tensor / "
                          f"per_channel results over codes of shape {tuple(out_shape)}; pass blocksize= for blockwise")
     out = torch.empty(out_shape, dtype=out_dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         st = _lib.lib().quanta_dequantize_affine(q.data_ptr(), int(bool(packed)), rows, cols, mode, B,
                                                  scale.data_ptr(), zp.data_ptr(), out.data_ptr(),
                                                  _host._DTYPE[out_dtype], _host.stream_ptr(dev))

@@ -61,8 +61,8 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
         return y.reshape(*x.shape[:-1], N)
     if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
-    with torch.cuda.device(dev):
-        ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+    with _host.device_guard(dev):
+        ws = _host.gemm_workspace(dev, _host.workspace_bytes(_lib.OP_GEMM, M, N))
         st = _lib.lib().quanta_gemm_wna16(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits, scale.data_ptr(),
                                           zp.data_ptr(), blocksize, bias.data_ptr() if bias is not None else None,
                                           y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
@@ -95,8 +95,8 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
     if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
-    with torch.cuda.device(dev):
-        ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+    with _host.device_guard(dev):
+        ws = _host.gemm_workspace(dev, _host.workspace_bytes(_lib.OP_GEMM, M, N))
         st = _lib.lib().quanta_gemm_wna16_scatter(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits,
                                                   scale.data_ptr(), zp.data_ptr(), blocksize,
                                                   bias.data_ptr() if bias is not None else None, arr, len(ptrs), ldy,
@@ -130,8 +130,8 @@ def linear_nf4a16(x, wq, absmax, bias=None, blocksize=64, out_features=None, in_
         return y.reshape(*x.shape[:-1], N)
     if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
-    with torch.cuda.device(dev):
-        ws = _host.gemm_workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_GEMM, M, N))
+    with _host.device_guard(dev):
+        ws = _host.gemm_workspace(dev, _host.workspace_bytes(_lib.OP_GEMM, M, N))
         st = _lib.lib().quanta_gemm_nf4a16(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), absmax.data_ptr(),
                                            blocksize, bias.data_ptr() if bias is not None else None, y.data_ptr(),
                                            M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
@@ -182,8 +182,8 @@ def int8_outlier_matmul(x, qw, cw, threshold=6.0, bias=None):
         return y.reshape(*x.shape[:-1], N)
     if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
-    with torch.cuda.device(dev):
-        ws = _host.workspace(dev, _lib.lib().quanta_workspace_bytes(_lib.OP_INT8_OUTLIER, M, K))
+    with _host.device_guard(dev):
+        ws = _host.workspace(dev, _host.workspace_bytes(_lib.OP_INT8_OUTLIER, M, K))
         st = _lib.lib().quanta_int8_outlier_matmul(x2.data_ptr(), _host.dtype_code(x2), qw.data_ptr(), cw.data_ptr(),
                                                    float(threshold), bias.data_ptr() if bias is not None else None,
                                                    y.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(),

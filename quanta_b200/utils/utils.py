@@ -22,7 +22,7 @@ def pack_4bit_tensor(tensor):
     n = q.numel()
     packed = torch.empty((n + 1) // 2, dtype=torch.uint8, device=q.device)
     if n:
-        with torch.cuda.device(q.device):
+        with _host.device_guard(q.device):
             st = _lib.lib().quanta_pack4(q.data_ptr(), n, packed.data_ptr(), _host.stream_ptr(q.device))
         _lib.check(st, "quanta_pack4")
     return packed, origin_shape
@@ -39,7 +39,7 @@ def unpack_4bit_tensor(packed_tensor):
         p = p.contiguous()
     out = torch.empty(p.numel() * 2, dtype=torch.uint8, device=p.device)
     if p.numel():
-        with torch.cuda.device(p.device):
+        with _host.device_guard(p.device):
             st = _lib.lib().quanta_unpack4(p.data_ptr(), p.numel(), out.data_ptr(), _host.stream_ptr(p.device))
         _lib.check(st, "quanta_unpack4")
     return out
@@ -196,7 +196,7 @@ def _convert_linear_fused(q_tensor, source_params, target_bits, target_type):
     q = q_tensor.detach()
     if not q.is_contiguous():
         q = q.contiguous()
-    with torch.cuda.device(dev):
+    with _host.device_guard(dev):
         out = torch.empty(q.shape, dtype=torch.uint8, device=dev)
         scale, zp = torch.empty((), dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev)
         ws = _host.workspace(dev, 256)
