@@ -5,39 +5,44 @@
 // 4096 x 14336 W4 matrix), so the kernel is built around the stream and keeps everything else
 // off its critical path:
 //
-//   * one persistent CTA per SM: a producer warp keeps a ring of TMA stages full (SWIZZLE_128B
-//     tiles of [128 rows x 128 B] codes plus the step's [128 x 4] scale / zero-point tiles on the
-//     same mbarrier; 120-160 KB in flight per SM from the first cycle to the last), 16 consumer
-//     warps drain it (warp = 32 weight rows x one 64-K block of every step, so a B fragment read
-//     from shared memory serves two row slabs).  The (row tile, 256-K step) units are cut into
-//     equal contiguous ranges, one per CTA (stream-K), so every SM streams for the same time
-//     whatever the shape;
-//   * codes are never dequantized one by one.  LOP3 drops a nibble pair into the mantissas of
-//     the 16-bit constant 128.0 (bf16) / 1024.0 (fp16) — exact integers C + n — and the warp-level
-//     tensor-core MMA (mma.sync m16n8k16, fp32 accumulate) forms raw = sum_k (C + n_k) x_k over one
-//     64-K block; scale and zero-point are applied once per block on the accumulators:
+//   * one persistent CTA per SM.  A producer thread keeps a ring of TMA stages full: SWIZZLE_128B
+//     tiles of [128 rows x 128 B] codes, the step's [128 x 4] scale / zero-point tiles and the step's
+//     activations [m_pad x 256] all on one mbarrier.  It starts before the rest of the CTA is set up
+//     and requests only three stages until the first one has landed (the TMA unit works on all of
+//     its outstanding copies at once: eight stages requested together by 148 SMs all complete
+//     together, ~4.5 K cycles later).  The (row tile, 256-K step) units are cut into equal
+//     contiguous ranges, one per CTA (stream-K), so every SM streams for the same time whatever
+//     the shape;
+//   * 16 consumer warps drain the ring (warp = 32 weight rows x one 64-K block of every step, so
+//     a B fragment read from shared memory serves two row slabs).  Codes are never dequantized one
+//     by one: LOP3 drops a nibble pair into the mantissas of the 16-bit constant 128.0 (bf16) /
+//     1024.0 (fp16) — exact integers C + n — and the warp-level tensor-core MMA (mma.sync m16n8k16,
+//     fp32 accumulate) forms raw = sum_k (C + n_k) x_k over one 64-K block; scale and zero-point are
+//     applied once per block on the accumulators:
 //         y += s * raw + (z - C s) * sum_k x_k
 //     i.e. 7 integer instructions per 8 weights + 2 FMAs per accumulator, instead of 19
 //     instructions per 8 weights for an element-wise dequantization.  The MMA's K order is free as
 //     long as both operands agree, so x is staged in the order the LOP3 pairs come out
 //     (k0,k4 | k1,k5 | k2,k6 | k3,k7) and no PRMT is needed.  8-bit codes go through
 //     PRMT -> fp32 (32768 + q) -> q -> packed 16-bit, exact as well;
-//   * x is streamed like the weights: while the consumers work on unit i, each of them fetches one
-//     16-byte chunk of unit i+2's activations, permutes it into MMA fragment order and adds it to a
-//     5-slot shared-memory ring together with the per-block sums of x (an mbarrier per slot counts
-//     the 16 warps; a slot is rewritten only after every warp has passed the unit that read it);
-//   * a CTA that covers only part of a row tile's K range stores an fp32 partial; the CTA that
-//     arrives last at the tile's counter sums the partials in a fixed order (deterministic), adds
-//     the bias and writes y — to every output buffer of a tensor-parallel call (peer-mapped
-//     buffers over NVLink).  The gpu-scope fences of that hand-over cost ~1.5 us each, so only a
-//     CTA's LAST segment publishes in line (the stream is over by then); the partial of its first
-//     segment is published by a separate warp while the consumers carry on streaming.
+//   * four staging warps turn the raw activations of a stage into MMA fragment order plus the
+//     per-block sums of x, in a 4-slot ring of their own (full / empty mbarriers), so the
+//     consumers' instruction stream is the weight path only;
+//   * a CTA that covers only part of a row tile's K range stores an fp32 partial and bumps the
+//     tile's counter with ONE fire-and-forget release; the CTA that owns the tile's last K steps
+//     is its reducer: once its own stream has ended it acquires the counter, sums the partials in
+//     CTA order (deterministic), adds the bias and writes y — to every output buffer of a
+//     tensor-parallel call (peer-mapped buffers over NVLink).  Nobody pays an atomic round trip
+//     between two fences at the end of the kernel (measured 5-9 K cycles per CTA); when a range
+//     holds whole tiles its partial segments are processed first, so the kernel ends on a plain
+//     store of y.
 //
 // The products use the exact fp32 value q*s + z of the weight (the tcgen05 path in gemm.cu rounds it
 // to the activation type first, like the reference's `.to(x.dtype)`); the difference is far inside
 // the 1e-2 tolerance of rows G1/G2.
 #include "common.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace quanta {
@@ -45,11 +50,12 @@ namespace quanta {
 constexpr int kSmRows = 128;               // weight rows per tile
 constexpr int kSmConsWarps = 16;           // warp w: rows 32 (w & 3) .. +32, block (w >> 2) of every step
 constexpr int kSmConsThreads = 32 * kSmConsWarps;
-constexpr int kSmThreads = kSmConsThreads + 64;   // + producer warp + publisher warp
+constexpr int kSmXWarps = 4;               // activation staging warps
+constexpr int kSmThreads = kSmConsThreads + 64 + 32 * kSmXWarps;   // + producer warp + publisher warp + staging warps
 constexpr int kSmStepK = 256;              // K per stage
 constexpr int kSmMaxRing = 8;
-constexpr int kSmXDist = 2;                // x of unit i + 2 is staged while unit i is computed
-constexpr int kSmXRing = 2 * kSmXDist + 1; // a warp at unit i may run next to a warp at unit i - 2
+constexpr int kSmXRing = 4;                // activation slots (one 256-K unit each)
+constexpr int kSmStartWindow = 3;          // stages requested before the first one has landed
 constexpr int kSmMaxOut = 8;
 constexpr int kSmCounterBytes = 64 * 1024; // same workspace header as gemm.cu (zero before, zero after)
 
@@ -64,7 +70,7 @@ struct SmallParams {
     int ldy, col0, n_out;
     int vec_y;              // 8-byte y stores are aligned in every output buffer
     int dbg;                // experiment switches (QUANTA_B200_SMALL_DBG): 1 no compute, 2 no x staging, 4 no epilogue
-    uint32_t stage_bytes;   // codes + scale tile + zero-point tile
+    uint32_t stage_bytes;   // codes + scale tile + zero-point tile + raw activations [m_pad x 256]
     uint32_t code_bytes;
     uint32_t x_off;         // x ring
     uint32_t x_slot_bytes;  // m_pad * 512 (chunks) + NB * 128 (block sums)
@@ -187,15 +193,59 @@ __device__ __forceinline__ int sm_cta_of_unit(unsigned int u, const SmallParams&
     return (int)c;
 }
 
-// Stream-K hand-over of one tile, publishing side (one thread): gpu-scope fences around the counter
-// update; returns 1 if this CTA arrived last (and resets the counter for the next call).
-__device__ __forceinline__ int sm_publish(unsigned int* counters, int tile, int contributors) {
-    __threadfence();
-    const unsigned int old = atomicAdd(&counters[tile], 1u);
-    __threadfence();
-    const int last = (old == (unsigned int)(contributors - 1)) ? 1 : 0;
-    if (last) counters[tile] = 0u;
-    return last;
+// The segments of a CTA's unit range [u0, u1) — a segment = this CTA's steps [s0, s1) of one row tile — in
+// PROCESSING order.  A segment that covers only part of a tile's K range ends with a hand-over through global
+// memory, a whole tile ends with a plain store of y.  So when the range holds whole tiles, the partial segments
+// (the tail of the first tile, the head of the last one) are processed FIRST and handed over while the stream
+// runs on, and the kernel ends on a whole tile.  With no whole tile in the range the natural order is kept.
+struct SmWalk {
+    unsigned int rb[3], re[3], u, S;
+    int nr, r;
+    __device__ __forceinline__ void init(unsigned int u0, unsigned int u1, unsigned int S_) {
+        S = S_; r = 0; nr = 0;
+        const unsigned int t0 = u0 / S, tl = (u1 - 1u) / S;
+        const bool f_part = (u0 - t0 * S) != 0u && t0 != tl;            // tail of the first tile
+        const bool l_part = (u1 - tl * S) != S && t0 != tl;             // head of the last tile
+        const unsigned int wb = f_part ? (t0 + 1u) * S : u0, we = l_part ? tl * S : u1;
+        if (t0 != tl && we > wb) {
+            if (l_part) { rb[nr] = tl * S; re[nr] = u1; ++nr; }
+            if (f_part) { rb[nr] = u0; re[nr] = (t0 + 1u) * S; ++nr; }
+            rb[nr] = wb; re[nr] = we; ++nr;
+        } else {
+            rb[0] = u0; re[0] = u1; nr = 1;
+        }
+        u = rb[0];
+    }
+    // next segment: steps [s0, s1) of `tile`; `final`: nothing follows it
+    __device__ __forceinline__ bool next(int& tile, int& s0, int& s1, bool& final) {
+        if (r < nr && u >= re[r]) { ++r; if (r < nr) u = rb[r]; }
+        if (r >= nr) return false;
+        const unsigned int t = u / S, b = u - t * S, left = re[r] - u;
+        tile = (int)t; s0 = (int)b;
+        s1 = (left < S - b) ? (int)(b + left) : (int)S;
+        u += (unsigned int)(s1 - s0);
+        final = (r == nr - 1) && u >= re[r];
+        return true;
+    }
+};
+
+// Stream-K hand-over of one tile.  The CTA that owns the tile's LAST K steps is its reducer; every other
+// contributor stores its partial and bumps the tile's counter with ONE fire-and-forget release
+// (red.release.gpu: the partial stores of the CTA — ordered before it by a CTA-level barrier — are visible to
+// whoever acquires the incremented value).  The reducer's own share of the tile is the first thing it
+// processes, so by the time its stream has ended the others have usually long arrived; it acquires the counter
+// (bounded spin; contributors have lower CTA indices and were dispatched earlier), resets it for the next call
+// and sums the partials.  A contributor never waits for anybody.
+__device__ __forceinline__ void sm_contribute(unsigned int* counters, int tile) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + tile) : "memory");
+}
+__device__ __forceinline__ void sm_await_contributors(unsigned int* counters, int tile, int others) {
+    unsigned int seen = 0, spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + tile) : "memory");
+        if (seen >= (unsigned int)others || ++spins > (1u << 22)) break;
+    }
+    counters[tile] = 0u;                                     // leave the workspace clean for the next call
 }
 
 // Sum the partials of every contributor of `tile` in CTA order (deterministic), add the bias, write y.
@@ -247,122 +297,140 @@ __device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __rest
 template <typename ACT, int BITS, int NB>
 __global__ void __launch_bounds__(kSmThreads, 1)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
-                  const __grid_constant__ CUtensorMap tmap_z, const ACT* __restrict__ x, const ACT* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_x, const ACT* __restrict__ bias,
                   unsigned int* __restrict__ counters, float* __restrict__ partial, const __grid_constant__ SmallParams p) {
     using T = SmTraits<ACT>;
     extern __shared__ __align__(1024) uint8_t sm_raw[];
-    constexpr int kChunks = 8 * NB * 32;                     // 16-byte x chunks per unit
-    constexpr int kXIter = (kChunks + kSmConsThreads - 1) / kSmConsThreads;
 
     const uint32_t smem = smem_u32(sm_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const uint32_t bars = smem + p.bar_off;                  // full[R] | empty[R] | xfull[kSmXRing] | flag
+    const uint32_t bars = smem + p.bar_off;                  // full[R] | empty[R] | xfull[XR] | xempty[XR]
     auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
     auto empty_bar = [&](int s) { return bars + (uint32_t)(kSmMaxRing + s) * 8u; };
     auto xfull_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + s) * 8u; };
-    const uint32_t flag_addr = bars + (uint32_t)(2 * kSmMaxRing + kSmXRing) * 8u;
+    auto xempty_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + kSmXRing + s) * 8u; };
 
     const unsigned int cta = blockIdx.x;
     const unsigned int u0 = p.U * cta / (unsigned int)p.G, u1 = p.U * (cta + 1u) / (unsigned int)p.G;
     const int n_units = (int)(u1 - u0);
     const int S = p.S;
-    const int tile0 = (int)(u0 / (unsigned int)S), step0 = (int)(u0 - (unsigned int)tile0 * (unsigned int)S);
-    // the CTA's first segment is published out of line iff it is a partial one and more work follows
-    const bool first_async = step0 != 0 && (unsigned int)(tile0 + 1) * (unsigned int)S < u1;
+    const int tile0 = (int)(u0 / (unsigned int)S);       // the first tile of the range owns partial slot 0
+    SmWalk walk;
+    walk.init(u0, u1, (unsigned int)S);
+    int tile, s0, s1;
+    bool final_seg;
 
-    if (tid == 0) {
+    // The producer initialises the weight ring itself, checks in at the CTA barrier WITHOUT waiting (bar.arrive)
+    // and starts streaming at once; everybody else sees all barriers after bar.sync.
+    if (tid == 32 * kSmConsWarps) {
+        prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z); prefetch_tensormap(&tmap_x);
         for (int s = 0; s < p.R; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar(s)), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar(s)), "r"(kSmConsWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar(s)), "r"(kSmConsWarps + kSmXWarps));
         }
-        for (int s = 0; s < kSmXRing; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xfull_bar(s)), "r"(kSmConsWarps));
         fence_barrier_init();
     }
-    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < kSmXRing; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xfull_bar(s)), "r"(kSmXWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xempty_bar(s)), "r"(kSmConsWarps));
+        }
+        fence_barrier_init();
+    }
+    if (warp == kSmConsWarps) {
+        __syncwarp();
+        asm volatile("barrier.arrive 0, %0;" ::"n"(kSmThreads) : "memory");
+    } else {
+        asm volatile("barrier.sync 0, %0;" ::"n"(kSmThreads) : "memory");
+    }
 
     if (warp == kSmConsWarps) {
         // ===== producer: keeps the ring full across tile boundaries =====
         if (lane == 0) {
-            prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z);
             const uint64_t pol = policy_evict_first();       // weights are streamed once
-            int slot = 0, tile = tile0, step = step0;
+            const uint64_t pol_x = policy_evict_last();      // activations are re-read by every row tile
+            int slot = 0, i = 0;
             uint32_t ph = 0;
-            for (int i = 0; i < n_units; ++i) {
-                if (p.dbg & 8) break;
-                if (i >= p.R) sm_bar_wait(empty_bar(slot), ph ^ 1u);
-                const uint32_t bar = full_bar(slot);
-                const uint32_t dst = smem + (uint32_t)slot * p.stage_bytes;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.stage_bytes) : "memory");
-                const int kb = step * kSmStepK, n0 = tile * kSmRows;
-                if (BITS == 4) {
-                    sm_tma_2d(dst, &tmap_w, bar, kb / 2, n0, pol);
-                } else {
-                    sm_tma_2d(dst, &tmap_w, bar, kb, n0, pol);
-                    sm_tma_2d(dst + 16384u, &tmap_w, bar, kb + 128, n0, pol);
+            while (walk.next(tile, s0, s1, final_seg)) {
+                for (int step = s0; step < s1; ++step, ++i) {
+                    if (p.dbg & 8) break;
+                    if (i >= p.R) sm_bar_wait(empty_bar(slot), ph ^ 1u);
+                    // start-up window (see the header): open the whole ring once the first stage has landed
+                    if (i == kSmStartWindow) sm_bar_wait(full_bar(0), 0u);
+                    const uint32_t bar = full_bar(slot);
+                    const uint32_t dst = smem + (uint32_t)slot * p.stage_bytes;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.stage_bytes) : "memory");
+                    const int kb = step * kSmStepK, n0 = tile * kSmRows;
+                    if (BITS == 4) {
+                        sm_tma_2d(dst, &tmap_w, bar, kb / 2, n0, pol);
+                    } else {
+                        sm_tma_2d(dst, &tmap_w, bar, kb, n0, pol);
+                        sm_tma_2d(dst + 16384u, &tmap_w, bar, kb + 128, n0, pol);
+                    }
+                    sm_tma_2d(dst + p.code_bytes, &tmap_s, bar, kb / 64, n0, pol);
+                    sm_tma_2d(dst + p.code_bytes + 2048u, &tmap_z, bar, kb / 64, n0, pol);
+                    // the step's activations [m_pad rows x 256 K] ride on the same barrier (rows past M arrive zero-filled)
+                    sm_tma_2d(dst + p.code_bytes + 4096u, &tmap_x, bar, kb, 0, pol_x);
+                    if (++slot == p.R) { slot = 0; ph ^= 1u; }
                 }
-                sm_tma_2d(dst + p.code_bytes, &tmap_s, bar, kb / 64, n0, pol);
-                sm_tma_2d(dst + p.code_bytes + 2048u, &tmap_z, bar, kb / 64, n0, pol);
-                if (++slot == p.R) { slot = 0; ph ^= 1u; }
-                if (++step == S) { step = 0; ++tile; }
             }
         }
         return;
     }
     if (warp == kSmConsWarps + 1) {
-        // ===== publisher: hands over the partial of the CTA's first segment while the stream runs on =====
-        if (first_async && !(p.dbg & 4)) {
+        // ===== publisher: releases the partial of every contributor segment that is not the CTA's last one while
+        //       the stream runs on (a segment that reaches the tile's last step makes this CTA the reducer: no release) =====
+        while (walk.next(tile, s0, s1, final_seg)) {
+            if (final_seg || s1 == S || (p.dbg & 4)) continue;
             asm volatile("bar.sync 2, 160;" ::: "memory");   // the 4 output warps have stored the partial
-            const unsigned int tu0 = (unsigned int)tile0 * (unsigned int)S;
-            const int c_first = sm_cta_of_unit(tu0, p), c_last = sm_cta_of_unit(tu0 + (unsigned int)S - 1u, p);
-            int last = 0;
-            if (lane == 0) last = sm_publish(counters, tile0, c_last - c_first + 1);
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) sm_fixup<ACT>(p, bias, partial, tile0, c_first, c_last, lane, 32);     // rare: the others finished first
+            if (lane == 0) sm_contribute(counters, tile);
         }
         return;
     }
 
-    // ===== consumers =====
-    const int gid = lane >> 2, tig = lane & 3;
-    const int rg = warp & 3, kq = warp >> 2;                 // rows 32 rg .. +32, block kq
-    // rows[sl][h]: slab sl (16 rows), MMA row gid + 8 h
-    int rows[2][2];
+    if (warp >= kSmConsWarps + 2) {
+        // ===== activation staging warps =====
+        // The unit's activations arrive with its weights (raw [m_pad x 256] rows behind the zero-point tile).  Chunk c
+        // (c = 32 xw + lane + 128 it): batch row m = c / 32, block (c / 8) & 3, 8 consecutive K values 8 (c & 7) of the
+        // block -> slot chunk (((nb 4 + blk) 2 + j) 32 + gid 4 + tig) with nb = m / 8, gid = m & 7, tig = (c & 7) / 2,
+        // j = c & 1: a consumer warp's B-fragment read of one (nb, blk, j) is 512 contiguous bytes.
+        constexpr int kChunks = 8 * NB * 32;                 // 16-byte x chunks per unit
+        constexpr int kPer = kChunks / (32 * kSmXWarps);
+        const int xw = warp - (kSmConsWarps + 2);
+        uint32_t xsrc[kPer], xdst[kPer], xsum_dst[kPer];
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl) { rows[sl][0] = (2 * rg + sl) * 16 + sm_row_of<BITS>(gid); rows[sl][1] = rows[sl][0] + 8; }
-
-    // x chunk c of a unit (c = tid + 512 it): batch row m = c / 32, block (c / 8) & 3, 8 consecutive K values
-    // 8 (c & 7) of the block -> ring slot chunk (((nb 4 + blk) 2 + j) 32 + gid 4 + tig) with
-    // nb = m / 8, gid = m & 7, tig = (c & 7) / 2, j = c & 1; a warp's B-fragment read of one
-    // (nb, blk, j) is 512 contiguous bytes.  Everything but the step is fixed per thread.
-    const ACT* xsrc[kXIter];
-    uint32_t xdst[kXIter], xsum_dst[kXIter];
-#pragma unroll
-    for (int it = 0; it < kXIter; ++it) {
-        const int c = tid + it * kSmConsThreads;
-        const int m = c >> 5, blk = (c >> 3) & 3, c8 = c & 7;
-        const int nb = m >> 3, g = m & 7, t = c8 >> 1, j = c8 & 1;
-        xsrc[it] = (c < kChunks && m < p.M) ? x + (int64_t)m * p.K + 8 * (c & 31) : nullptr;
-        xdst[it] = (uint32_t)((((nb * 4 + blk) * 2 + j) * 32 + g * 4 + t) * 16);
-        xsum_dst[it] = (uint32_t)(NB * 4096 + ((nb * 4 + blk) * 8 + g) * 4);
-    }
-    auto x_fetch = [&](int step, uint4* xv) {
-#pragma unroll
-        for (int it = 0; it < kXIter; ++it) {
-            xv[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (xsrc[it] != nullptr) xv[it] = __ldg(reinterpret_cast<const uint4*>(xsrc[it] + step * kSmStepK));
+        for (int it = 0; it < kPer; ++it) {
+            const int c = 32 * xw + lane + 32 * kSmXWarps * it;
+            const int m = c >> 5, blk = (c >> 3) & 3, c8 = c & 7;
+            const int nb = m >> 3, g = m & 7, t = c8 >> 1, j = c8 & 1;
+            xsrc[it] = p.code_bytes + 4096u + (uint32_t)(c * 16);
+            xdst[it] = (uint32_t)((((nb * 4 + blk) * 2 + j) * 32 + g * 4 + t) * 16);
+            xsum_dst[it] = (uint32_t)(NB * 4096 + ((nb * 4 + blk) * 8 + g) * 4);
         }
-    };
-    auto x_store = [&](int xslot_idx, const uint4* xv) {
-        const uint32_t slot = smem + p.x_off + (uint32_t)xslot_idx * p.x_slot_bytes;
+        const bool x_on = !(p.dbg & 2), w_on = !(p.dbg & 8);
+        int xs = 0, ws_ = 0;
+        uint32_t ph = 0, wph_ = 0;
+        for (int i = 0; i < n_units; ++i) {
+            if (w_on) sm_bar_wait(full_bar(ws_), wph_);
+            if (!x_on) {                                     // experiment switch: release the stage, stage nothing
+                __syncwarp();
+                if (lane == 0) sm_bar_arrive(empty_bar(ws_));
+                if (++ws_ == p.R) { ws_ = 0; wph_ ^= 1u; }
+                continue;
+            }
+            if (i >= kSmXRing) sm_bar_wait(xempty_bar(xs), ph ^ 1u);
+            const uint32_t stage = smem + (uint32_t)ws_ * p.stage_bytes;
+            const uint32_t slot = smem + p.x_off + (uint32_t)xs * p.x_slot_bytes;
+            uint4 raw[kPer];
 #pragma unroll
-        for (int it = 0; it < kXIter; ++it) {
-            if (tid + it * kSmConsThreads < kChunks) {       // warp-uniform: kChunks is a multiple of 256
-                uint4 v = xv[it];
+            for (int it = 0; it < kPer; ++it) raw[it] = sm_lds128(stage + xsrc[it]);
+#pragma unroll
+            for (int it = 0; it < kPer; ++it) {
+                uint4 v = raw[it];
                 const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
                 float sum = 0.0f;
-                if (sizeof(ACT) == 2 && SmTraits<ACT>::kOffset == 128.0f) {
+                if (SmTraits<ACT>::kOffset == 128.0f) {
                     // bf16 -> fp32 is a shift / mask
 #pragma unroll
                     for (int q = 0; q < 4; ++q) sum += __uint_as_float(w4[q] << 16) + __uint_as_float(w4[q] & 0xFFFF0000u);
@@ -385,16 +453,21 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 sm_sts128(slot + xdst[it], v);
                 if ((lane & 7) == 0) sm_sts32(slot + xsum_dst[it], sum);
             }
+            __syncwarp();
+            if (lane == 0) { sm_bar_arrive(xfull_bar(xs)); sm_bar_arrive(empty_bar(ws_)); }
+            if (++xs == kSmXRing) { xs = 0; ph ^= 1u; }
+            if (++ws_ == p.R) { ws_ = 0; wph_ ^= 1u; }
         }
-        __syncwarp();
-        if (lane == 0) sm_bar_arrive(xfull_bar(xslot_idx));
-    };
-    auto step_after = [&](int step, int d) { int s = step + d; while (s >= S) s -= S; return s; };
-
-    if (!(p.dbg & 2)) {
-        uint4 xv[kXIter];
-        for (int i = 0; i < kSmXDist && i < n_units; ++i) { x_fetch(step_after(step0, i), xv); x_store(i, xv); }
+        return;
     }
+
+    // ===== consumers =====
+    const int gid = lane >> 2, tig = lane & 3;
+    const int rg = warp & 3, kq = warp >> 2;                 // rows 32 rg .. +32, block kq
+    // rows[sl][h]: slab sl (16 rows), MMA row gid + 8 h
+    int rows[2][2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) { rows[sl][0] = (2 * rg + sl) * 16 + sm_row_of<BITS>(gid); rows[sl][1] = rows[sl][0] + 8; }
 
     const bool do_compute = !(p.dbg & 1), do_x = !(p.dbg & 2), do_epi = !(p.dbg & 4), do_wait = !(p.dbg & 8);
     // Per-thread shared-memory offsets (the block b = kq is fixed per warp; rows + 8 / + 16 keep the swizzle
@@ -412,116 +485,105 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) { tot[sl][nb][0] = tot[sl][nb][1] = tot[sl][nb][2] = tot[sl][nb][3] = 0.0f; }
-    int wslot = 0, xs_cur = 0, xs_ahead = kSmXDist % kSmXRing;
+    int wslot = 0, xs_cur = 0, red_tile = -1;
     uint32_t wph = 0, xph = 0;
-    int tile = tile0, step = step0, step_ahead = step_after(step0, kSmXDist);
-    int seg_s0 = step0;                                      // first step of the current tile segment
 
-    for (int i = 0; i < n_units; ++i) {
-        uint4 xv[kXIter];
-        const bool ahead = i + kSmXDist < n_units && do_x;
-        if (ahead) x_fetch(step_ahead, xv);
+    while (walk.next(tile, s0, s1, final_seg)) {
+        for (int step = s0; step < s1; ++step) {
+            if (do_wait) sm_bar_wait(full_bar(wslot), wph);
+            if (do_x) sm_bar_wait(xfull_bar(xs_cur), xph);
 
-        if (do_wait) sm_bar_wait(full_bar(wslot), wph);
-        if (do_x) sm_bar_wait(xfull_bar(xs_cur), xph);
-
-        if (do_compute) {
-            const uint32_t sb = smem + (uint32_t)wslot * p.stage_bytes;
-            const uint32_t xs_base = smem + (uint32_t)xs_cur * p.x_slot_bytes;
-            // ---- every shared-memory read of the unit goes out first (they are ordered asm statements;
-            //      the arithmetic below is free for the compiler to interleave) ----
-            uint32_t wraw[2][2][BITS == 4 ? 2 : 4];          // [slab][row half][words]
+            if (do_compute) {
+                const uint32_t sb = smem + (uint32_t)wslot * p.stage_bytes;
+                const uint32_t xs_base = smem + (uint32_t)xs_cur * p.x_slot_bytes;
+                // ---- every shared-memory read of the unit goes out first (they are ordered asm statements;
+                //      the arithmetic below is free for the compiler to interleave) ----
+                uint32_t wraw[2][2][BITS == 4 ? 2 : 4];      // [slab][row half][words]
 #pragma unroll
-            for (int sl = 0; sl < 2; ++sl)
+                for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t wa = sb + w_off + (uint32_t)(sl * 2048 + h * 1024);
-                    if (BITS == 4) {
-                        const uint2 w = sm_lds64(wa);
-                        wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y;
-                    } else {
-                        const uint4 w = sm_lds128(wa);
-                        wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y; wraw[sl][h][BITS == 4 ? 0 : 2] = w.z; wraw[sl][h][BITS == 4 ? 1 : 3] = w.w;
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t wa = sb + w_off + (uint32_t)(sl * 2048 + h * 1024);
+                        if (BITS == 4) {
+                            const uint2 w = sm_lds64(wa);
+                            wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y;
+                        } else {
+                            const uint4 w = sm_lds128(wa);
+                            wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y; wraw[sl][h][BITS == 4 ? 0 : 2] = w.z; wraw[sl][h][BITS == 4 ? 1 : 3] = w.w;
+                        }
+                    }
+                uint4 xb[NB][2];
+                uint2 xs2[NB];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    xb[nb][0] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096));
+                    xb[nb][1] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096 + 512));
+                    xs2[nb] = sm_lds64(xs_base + xs_off + (uint32_t)(nb * 128));
+                }
+                float sc[2][2], zc[2][2];
+                const float off = BITS == 4 ? T::kOffset : 0.0f;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        sc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128));
+                        zc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128 + 2048));
+                    }
+                // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
+                //      are independent (2 slabs x NB accumulators) ----
+                float c[2][NB][4];
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) { c[sl][nb][0] = c[sl][nb][1] = c[sl][nb][2] = c[sl][nb][3] = 0.0f; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t a[2][4];                        // {row lo, row+8 lo, row hi, row+8 hi}
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) {
+                        if (BITS == 4) {
+                            // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k
+                            const uint32_t w0 = wraw[sl][0][k >> 1] >> (8 * (k & 1)), w1 = wraw[sl][1][k >> 1] >> (8 * (k & 1));
+                            a[sl][0] = sm_and_or(w0, 0x000F000Fu, T::kMagic);
+                            a[sl][1] = sm_and_or(w1, 0x000F000Fu, T::kMagic);
+                            a[sl][2] = sm_and_or(w0 >> 4, 0x000F000Fu, T::kMagic);
+                            a[sl][3] = sm_and_or(w1 >> 4, 0x000F000Fu, T::kMagic);
+                        } else {
+                            uint32_t p0[2], p1[2];
+                            sm_pairs8<ACT>(wraw[sl][0][k], p0); sm_pairs8<ACT>(wraw[sl][1][k], p1);
+                            a[sl][0] = p0[0]; a[sl][1] = p1[0]; a[sl][2] = p0[1]; a[sl][3] = p1[1];
+                        }
+                    }
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const uint4 xv4 = xb[nb][k >> 1];
+                        const uint32_t b0 = (k & 1) ? xv4.z : xv4.x, b1 = (k & 1) ? xv4.w : xv4.y;
+#pragma unroll
+                        for (int sl = 0; sl < 2; ++sl) T::mma(c[sl][nb], a[sl], b0, b1);
                     }
                 }
-            uint4 xb[NB][2];
-            uint2 xs2[NB];
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                xb[nb][0] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096));
-                xb[nb][1] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096 + 512));
-                xs2[nb] = sm_lds64(xs_base + xs_off + (uint32_t)(nb * 128));
-            }
-            float sc[2][2], zc[2][2];
-            const float off = BITS == 4 ? T::kOffset : 0.0f;
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    sc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128));
-                    zc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128 + 2048));
-                }
-            // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
-            //      are independent (2 slabs x NB accumulators) ----
-            float c[2][NB][4];
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) { c[sl][nb][0] = c[sl][nb][1] = c[sl][nb][2] = c[sl][nb][3] = 0.0f; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t a[2][4];                            // {row lo, row+8 lo, row hi, row+8 hi}
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
-                    if (BITS == 4) {
-                        // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k
-                        const uint32_t w0 = wraw[sl][0][k >> 1] >> (8 * (k & 1)), w1 = wraw[sl][1][k >> 1] >> (8 * (k & 1));
-                        a[sl][0] = sm_and_or(w0, 0x000F000Fu, T::kMagic);
-                        a[sl][1] = sm_and_or(w1, 0x000F000Fu, T::kMagic);
-                        a[sl][2] = sm_and_or(w0 >> 4, 0x000F000Fu, T::kMagic);
-                        a[sl][3] = sm_and_or(w1 >> 4, 0x000F000Fu, T::kMagic);
-                    } else {
-                        uint32_t p0[2], p1[2];
-                        sm_pairs8<ACT>(wraw[sl][0][k], p0); sm_pairs8<ACT>(wraw[sl][1][k], p1);
-                        a[sl][0] = p0[0]; a[sl][1] = p1[0]; a[sl][2] = p0[1]; a[sl][3] = p1[1];
+                    const float z0 = __fmaf_rn(-off, sc[sl][0], zc[sl][0]), z1 = __fmaf_rn(-off, sc[sl][1], zc[sl][1]);
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const float xs_a = __uint_as_float(xs2[nb].x), xs_b = __uint_as_float(xs2[nb].y);
+                        tot[sl][nb][0] = __fmaf_rn(sc[sl][0], c[sl][nb][0], __fmaf_rn(z0, xs_a, tot[sl][nb][0]));
+                        tot[sl][nb][1] = __fmaf_rn(sc[sl][0], c[sl][nb][1], __fmaf_rn(z0, xs_b, tot[sl][nb][1]));
+                        tot[sl][nb][2] = __fmaf_rn(sc[sl][1], c[sl][nb][2], __fmaf_rn(z1, xs_a, tot[sl][nb][2]));
+                        tot[sl][nb][3] = __fmaf_rn(sc[sl][1], c[sl][nb][3], __fmaf_rn(z1, xs_b, tot[sl][nb][3]));
                     }
                 }
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    const uint4 xv4 = xb[nb][k >> 1];
-                    const uint32_t b0 = (k & 1) ? xv4.z : xv4.x, b1 = (k & 1) ? xv4.w : xv4.y;
-#pragma unroll
-                    for (int sl = 0; sl < 2; ++sl) T::mma(c[sl][nb], a[sl], b0, b1);
-                }
             }
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-                const float z0 = __fmaf_rn(-off, sc[sl][0], zc[sl][0]), z1 = __fmaf_rn(-off, sc[sl][1], zc[sl][1]);
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    const float xs_a = __uint_as_float(xs2[nb].x), xs_b = __uint_as_float(xs2[nb].y);
-                    tot[sl][nb][0] = __fmaf_rn(sc[sl][0], c[sl][nb][0], __fmaf_rn(z0, xs_a, tot[sl][nb][0]));
-                    tot[sl][nb][1] = __fmaf_rn(sc[sl][0], c[sl][nb][1], __fmaf_rn(z0, xs_b, tot[sl][nb][1]));
-                    tot[sl][nb][2] = __fmaf_rn(sc[sl][1], c[sl][nb][2], __fmaf_rn(z1, xs_a, tot[sl][nb][2]));
-                    tot[sl][nb][3] = __fmaf_rn(sc[sl][1], c[sl][nb][3], __fmaf_rn(z1, xs_b, tot[sl][nb][3]));
-                }
-            }
+            // every lane's reads of the stage have been consumed by the instructions above
+            __syncwarp();
+            if (lane == 0) { sm_bar_arrive(empty_bar(wslot)); if (do_x) sm_bar_arrive(xempty_bar(xs_cur)); }
+            if (++wslot == p.R) { wslot = 0; wph ^= 1u; }
+            if (++xs_cur == kSmXRing) { xs_cur = 0; xph ^= 1u; }
         }
-        // every lane's reads of the stage have been consumed by the instructions above
-        __syncwarp();
-        if (lane == 0) sm_bar_arrive(empty_bar(wslot));
-        if (++wslot == p.R) { wslot = 0; wph ^= 1u; }
-        if (++xs_cur == kSmXRing) { xs_cur = 0; xph ^= 1u; }
-
-        if (ahead) x_store(xs_ahead, xv);
-        if (++xs_ahead == kSmXRing) xs_ahead = 0;
-        if (++step_ahead == S) step_ahead = 0;
-
-        const bool seg_end = step == S - 1 || i == n_units - 1;
-        if (seg_end && do_epi) {
-            // ===== end of this CTA's segment [seg_s0, step] of `tile`: the 4 K quarters meet in shared memory =====
-            const bool whole = seg_s0 == 0 && step == S - 1;
-            const bool final_seg = i == n_units - 1;
+        if (do_epi) {
+            // ===== end of this CTA's segment [s0, s1) of `tile`: the 4 K quarters meet in shared memory =====
+            const bool whole = s0 == 0 && s1 == S;
             const uint32_t red = smem + p.red_off + (uint32_t)(rg * (2 * NB * 4) * 128 + lane * 4);
             const uint32_t red_group = (uint32_t)(4 * 2 * NB * 4 * 128);
             if (kq > 0) {
@@ -578,8 +640,8 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 __stcg(mine + (8 * nb + 2 * tig + (q & 1)) * kSmRows + rows[sl][q >> 1], tot[sl][nb][q]);
-                    if (!final_seg) {
-                        // more work follows: the publisher warp takes the hand-over from here
+                    if (!final_seg && s1 != S) {
+                        // a contributor segment with more work behind it: the publisher warp releases it
                         __syncwarp();
                         asm volatile("bar.arrive 2, 160;" ::: "memory");
                     }
@@ -589,25 +651,18 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { tot[sl][nb][0] = tot[sl][nb][1] = tot[sl][nb][2] = tot[sl][nb][3] = 0.0f; }
-            if (!whole && final_seg) {
-                // the stream is over: publish in line; the CTA that arrives last reduces every contributor's partial
-                const unsigned int tu0 = (unsigned int)tile * (unsigned int)S;
-                const int c_first = sm_cta_of_unit(tu0, p), c_last = sm_cta_of_unit(tu0 + (unsigned int)S - 1u, p);
-                sm_cons_sync();
-                if (tid == 0) {
-                    const int last = sm_publish(counters, tile, c_last - c_first + 1);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_addr), "r"(last) : "memory");
-                }
-                sm_cons_sync();
-                int last;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag_addr));
-                if (last) sm_fixup<ACT>(p, bias, partial, tile, c_first, c_last, tid, kSmConsThreads);
-            } else {
-                sm_cons_sync();                              // red is reused by the next segment
-            }
-            seg_s0 = 0;
+            if (!whole && s1 == S) red_tile = tile;          // this CTA reduces the tile once its stream has ended
+            sm_cons_sync();                                  // red is reused by the next segment; the partial stores are done
+            if (!whole && final_seg && s1 != S && tid == 0) sm_contribute(counters, tile);
         }
-        if (++step == S) { step = 0; ++tile; }
+    }
+    if (red_tile >= 0 && do_epi) {
+        // ===== reducer duty: the other contributors' partials (lower CTA indices) =====
+        const unsigned int tu0 = (unsigned int)red_tile * (unsigned int)S;
+        const int c_first = sm_cta_of_unit(tu0, p), c_last = (int)cta;
+        if (tid == 0) sm_await_contributors(counters, red_tile, c_last - c_first);
+        sm_cons_sync();
+        sm_fixup<ACT>(p, bias, partial, red_tile, c_first, c_last, tid, kSmConsThreads);
     }
 }
 
@@ -663,7 +718,7 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     if (small_tuning().ctas) sms = small_tuning().ctas < sms ? small_tuning().ctas : sms;
     p.G = (int)(p.U < (unsigned int)sms ? p.U : (unsigned int)sms);
     p.code_bytes = BITS == 4 ? 16384u : 32768u;
-    p.stage_bytes = p.code_bytes + 4096u;
+    p.stage_bytes = p.code_bytes + 4096u + (uint32_t)p.m_pad * 512u;       // codes | scales | zero-points | activations
     p.x_slot_bytes = (uint32_t)(NB * 4096 + NB * 128);
     const uint32_t x_bytes = (uint32_t)kSmXRing * p.x_slot_bytes;
     const uint32_t red_bytes = (uint32_t)(3 * 4 * 2 * NB * 4 * 128);
@@ -706,9 +761,13 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
                             CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
 
+    CUtensorMap tmap_x;
+    rc = make_tensor_map_2d(&tmap_x, SmTraits<ACT>::kOffset == 128.0f ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                            2, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kSmStepK, (uint32_t)p.m_pad, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
     auto kern = gemm_small_kernel<ACT, BITS, NB>;
     if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
-    kern<<<dim3((unsigned)p.G), kSmThreads, (size_t)smem, st>>>(tmap_w, tmap_s, tmap_z, x, bias, counters, partial, p);
+    kern<<<dim3((unsigned)p.G), kSmThreads, (size_t)smem, st>>>(tmap_w, tmap_s, tmap_z, tmap_x, bias, counters, partial, p);
     return cuda_status(cudaGetLastError());
 }
 
