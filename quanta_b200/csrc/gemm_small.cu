@@ -352,32 +352,55 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const uint64_t pol_x = policy_evict_last();      // activations are re-read by every row tile
             int slot = 0, i = 0;
             uint32_t ph = 0;
+            // Programmatic dependent launch: this grid may start while the previous kernel on the stream is still in
+            // its tail.  The weights do not depend on it, so the first stages' codes / scales / zero-points are
+            // requested at once; the activations (the previous kernel's output, in a chain of layers) and every
+            // global write of this kernel wait for griddepcontrol.wait — a no-op in an ordinary launch.
+            int pend_step[kSmStartWindow], npend = 0;
+            bool waited = false;
+            auto issue_weights = [&](uint32_t bar, uint32_t dst, int kb, int n0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.stage_bytes) : "memory");
+                if (BITS == 4) {
+                    sm_tma_2d(dst, &tmap_w, bar, kb / 2, n0, pol);
+                } else {
+                    sm_tma_2d(dst, &tmap_w, bar, kb, n0, pol);
+                    sm_tma_2d(dst + 16384u, &tmap_w, bar, kb + 128, n0, pol);
+                }
+                sm_tma_2d(dst + p.code_bytes, &tmap_s, bar, kb / 64, n0, pol);
+                sm_tma_2d(dst + p.code_bytes + 2048u, &tmap_z, bar, kb / 64, n0, pol);
+            };
+            auto dependency_wait = [&]() {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                waited = true;
+                // the activations [m_pad rows x 256 K] of the stages requested so far (rows past M arrive zero-filled)
+                for (int k = 0; k < npend; ++k)
+                    sm_tma_2d(smem + (uint32_t)k * p.stage_bytes + p.code_bytes + 4096u, &tmap_x, full_bar(k), pend_step[k] * kSmStepK, 0, pol_x);
+            };
             while (walk.next(tile, s0, s1, final_seg)) {
                 for (int step = s0; step < s1; ++step, ++i) {
                     if (p.dbg & 8) break;
+                    if (i == kSmStartWindow) {
+                        // start-up window (see the header): open the whole ring once the first stage has landed
+                        dependency_wait();
+                        sm_bar_wait(full_bar(0), 0u);
+                    }
                     if (i >= p.R) sm_bar_wait(empty_bar(slot), ph ^ 1u);
-                    // start-up window (see the header): open the whole ring once the first stage has landed
-                    if (i == kSmStartWindow) sm_bar_wait(full_bar(0), 0u);
                     const uint32_t bar = full_bar(slot);
                     const uint32_t dst = smem + (uint32_t)slot * p.stage_bytes;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.stage_bytes) : "memory");
-                    const int kb = step * kSmStepK, n0 = tile * kSmRows;
-                    if (BITS == 4) {
-                        sm_tma_2d(dst, &tmap_w, bar, kb / 2, n0, pol);
-                    } else {
-                        sm_tma_2d(dst, &tmap_w, bar, kb, n0, pol);
-                        sm_tma_2d(dst + 16384u, &tmap_w, bar, kb + 128, n0, pol);
-                    }
-                    sm_tma_2d(dst + p.code_bytes, &tmap_s, bar, kb / 64, n0, pol);
-                    sm_tma_2d(dst + p.code_bytes + 2048u, &tmap_z, bar, kb / 64, n0, pol);
-                    // the step's activations [m_pad rows x 256 K] ride on the same barrier (rows past M arrive zero-filled)
-                    sm_tma_2d(dst + p.code_bytes + 4096u, &tmap_x, bar, kb, 0, pol_x);
+                    issue_weights(bar, dst, step * kSmStepK, tile * kSmRows);
+                    if (waited) sm_tma_2d(dst + p.code_bytes + 4096u, &tmap_x, bar, step * kSmStepK, 0, pol_x);
+                    else pend_step[npend++] = step;
                     if (++slot == p.R) { slot = 0; ph ^= 1u; }
                 }
             }
+            if (!waited) dependency_wait();
         }
         return;
     }
+    // Let the next kernel on the stream start its own prologue as soon as this grid's CTAs make room (its weights do
+    // not depend on us); every other warp orders its global accesses behind the previous kernel.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp == kSmConsWarps + 1) {
         // ===== publisher: releases the partial of every contributor segment that is not the CTA's last one while
         //       the stream runs on (a segment that reaches the tile's last step makes this CTA the reducer: no release) =====
@@ -668,14 +691,15 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
 // ---- host side --------------------------------------------------------------
 
-struct SmallTuning { int ring; int max_m; int ctas; int dbg; };
+struct SmallTuning { int ring; int max_m; int ctas; int dbg; int pdl; };
 static SmallTuning small_tuning() {
     static const SmallTuning t = []() {
-        SmallTuning v{0, 16, 0, 0};
+        SmallTuning v{0, 16, 0, 0, 1};
         if (const char* e = getenv("QUANTA_B200_SMALL_RING")) { int s = atoi(e); if (s >= 2 && s <= kSmMaxRing) v.ring = s; }
         if (const char* e = getenv("QUANTA_B200_SMALL_MAX_M")) { int m = atoi(e); if (m >= 0 && m <= 16) v.max_m = m; }
         if (const char* e = getenv("QUANTA_B200_SMALL_CTAS")) { int c = atoi(e); if (c >= 1 && c <= kNumSMs) v.ctas = c; }
         if (const char* e = getenv("QUANTA_B200_SMALL_DBG")) v.dbg = atoi(e);
+        if (const char* e = getenv("QUANTA_B200_SMALL_PDL")) v.pdl = atoi(e) != 0;
         return v;
     }();
     return t;
@@ -767,8 +791,18 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     if (rc) return rc;
     auto kern = gemm_small_kernel<ACT, BITS, NB>;
     if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
-    kern<<<dim3((unsigned)p.G), kSmThreads, (size_t)smem, st>>>(tmap_w, tmap_s, tmap_z, tmap_x, bias, counters, partial, p);
-    return cuda_status(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.G);
+    cfg.blockDim = dim3(kSmThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = small_tuning().pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_s, tmap_z, tmap_x, bias, counters, partial, p);
+    return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 template <typename ACT, int BITS>
