@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) dequant_flat_kernel(const uint8_t* __rest
                                                            int64_t block, const float* __restrict__ scale,
                                                            const float* __restrict__ zp, OUT* __restrict__ out,
                                                            const int* __restrict__ flag, float off) {
+    pdl_enter();
     const bool sym = CONV == kDqB && flag[0] != 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // per-tensor parameters (block == 0) are fetched and prepared once
@@ -213,8 +214,9 @@ static int dequant_launch(const uint8_t* q, int64_t rows, int64_t cols, int mode
         if (n4 > 0) {
             int64_t want = (n4 + 255) / 256;
             int64_t cap = (int64_t)kNumSMs * 8 * 4;
-            dequant_flat_kernel<OUT, PACKED, CONV><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
-                q, n4, shift_of(block), mode == QUANTA_MODE_TENSOR ? 0 : block, scale, zp, out, flag, off);
+            cudaError_t e = launch_pdl(dequant_flat_kernel<OUT, PACKED, CONV>, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, st,
+                                       q, n4, shift_of(block), mode == QUANTA_MODE_TENSOR ? (int64_t)0 : block, scale, zp, out, flag, off);
+            if (e != cudaSuccess) return (int)e;
         }
         done = n4 * 4;
     }

@@ -22,6 +22,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // 16 codes (uint4) -> 8 bytes (uint2) per vector.
 template <bool HI>
 __global__ void __launch_bounds__(256) pack4_vec_kernel(const uint4* __restrict__ q, int64_t nvec, uint2* __restrict__ out) {
+    pdl_enter();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto pack = [](uint4 v) {
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) pack4_tail_kernel(const uint8_t* __restri
 // 8 packed bytes (uint2) -> 16 codes (uint4) per vector.
 template <bool HI>
 __global__ void __launch_bounds__(256) unpack4_vec_kernel(const uint2* __restrict__ p, int64_t nvec, uint4* __restrict__ out) {
+    pdl_enter();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto unpack = [](uint2 v) {
@@ -97,8 +99,8 @@ static int pack4_launch(const uint8_t* q, int64_t n, uint8_t* packed, void* stre
     const bool ok = (reinterpret_cast<uintptr_t>(q) % 16 == 0) && (reinterpret_cast<uintptr_t>(packed) % 8 == 0);
     const int64_t nvec = ok ? n / 16 : 0;
     if (nvec > 0)
-        pack4_vec_kernel<HI><<<grid_for(nvec), 256, 0, st>>>(reinterpret_cast<const uint4*>(q), nvec,
-                                                            reinterpret_cast<uint2*>(packed));
+        launch_pdl(pack4_vec_kernel<HI>, dim3(grid_for(nvec)), dim3(256), 0, st, reinterpret_cast<const uint4*>(q), nvec,
+                   reinterpret_cast<uint2*>(packed));
     const int64_t start = nvec * 16;
     if (start < n) {
         const int64_t pairs = (n - start + 1) / 2;
@@ -115,8 +117,8 @@ static int unpack4_launch(const uint8_t* packed, int64_t nbytes, uint8_t* out, v
     const bool ok = (reinterpret_cast<uintptr_t>(packed) % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
     const int64_t nvec = ok ? nbytes / 8 : 0;
     if (nvec > 0)
-        unpack4_vec_kernel<HI><<<grid_for(nvec), 256, 0, st>>>(reinterpret_cast<const uint2*>(packed), nvec,
-                                                              reinterpret_cast<uint4*>(out));
+        launch_pdl(unpack4_vec_kernel<HI>, dim3(grid_for(nvec)), dim3(256), 0, st, reinterpret_cast<const uint2*>(packed), nvec,
+                   reinterpret_cast<uint4*>(out));
     const int64_t start = nvec * 8;
     if (start < nbytes)
         unpack4_tail_kernel<HI><<<(unsigned)((nbytes - start + 255) / 256), 256, 0, st>>>(packed, start, nbytes, out);

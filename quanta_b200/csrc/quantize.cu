@@ -397,6 +397,7 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
         fence_barrier_init();
     }
     __syncthreads();
+    pdl_enter();                                           // the set-up above may overlap the previous kernel's tail
 
     if (warp == kConsumerWarps) {
         // ===== producer warp: one lane streams tiles into the ring =====
@@ -1272,6 +1273,7 @@ quantize_rows_tma_multi_kernel(const __grid_constant__ MultiArgs a, int log2_lan
         fence_barrier_init();
     }
     __syncthreads();
+    pdl_enter();                                           // the set-up above may overlap the previous kernel's tail
 
     if (warp == kConsumerWarps) {
         if (lane == 0) {
@@ -1550,8 +1552,9 @@ static int launch_rows_tma_impl(const CUtensorMap& tmap, int64_t n_rows, int lan
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
     // DYN: one CTA per tile; resident CTAs steal the not-yet-launched ones (cluster launch control)
     const unsigned grid = DYN ? (unsigned)n_tiles : (unsigned)grid_for_tiles(n_tiles);
-    kern<<<grid, kTmaThreads, smem, st>>>(tmap, n_rows, log2_of(lanes_per_block), q, scale, zp, ws, nparts);
-    return cuda_status(cudaGetLastError());
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kTmaThreads), (size_t)smem, st, tmap, n_rows, log2_of(lanes_per_block), q, scale, zp,
+                               ws, nparts);
+    return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 template <typename T, int BITS, bool PACK, int CONV, bool BLOCKWISE>
@@ -1807,7 +1810,9 @@ static int quantize_block_batch_t(const void* const* xs, const int64_t* numels, 
     args.tile_base[0] = 0;
     auto flush = [&]() -> int {
         if (args.count == 0) return QUANTA_OK;
-        kern<<<(unsigned)args.tile_base[args.count], kTmaThreads, smem, st>>>(args, log2_of(block / kRowElems));
+        cudaError_t le = launch_pdl(kern, dim3((unsigned)args.tile_base[args.count]), dim3(kTmaThreads), (size_t)smem, st, args,
+                                    log2_of(block / kRowElems));
+        if (le != cudaSuccess) return (int)le;
         args.count = 0;
         args.tile_base[0] = 0;
         return cuda_status(cudaGetLastError());
