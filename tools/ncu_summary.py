@@ -2,7 +2,7 @@
 
   python tools/ncu_summary.py launches <launches.csv> <out.txt>   # per-kernel count / total / share
   python tools/ncu_summary.py report   <file.ncu-rep> <out.txt>   # key metrics of each profiled launch
-  python tools/ncu_summary.py traffic  <file.ncu-rep> <out.json> [algorithmic bytes per launch] [note]
+  python tools/ncu_summary.py traffic  <file.ncu-rep> <out.json> [algorithmic bytes per launch | "xCTA:<bytes per CTA>"] [note]
                                                                    # DRAM bytes per launch (bench.py reads this)
 """
 import csv
@@ -85,10 +85,19 @@ def traffic(path, out, algorithmic=None, note=""):
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         rd, wr = val(d, "dram__bytes_read.sum"), val(d, "dram__bytes_write.sum")
+        alg = None
+        if algorithmic:
+            if str(algorithmic).startswith("xCTA:"):            # algorithmic bytes = CTAs of the launch x bytes per CTA (one tile each)
+                ctas = 1
+                for v in re.findall(r"\d+", d["Grid Size"]):
+                    ctas *= int(v)
+                alg = ctas * float(str(algorithmic)[5:])
+            else:
+                alg = float(algorithmic)
         recs.append({"kernel": short(d["Kernel Name"]), "grid": d["Grid Size"], "block": d["Block Size"],
                      "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
                      "duration_us_under_ncu": val(d, "gpu__time_duration.sum"),
-                     "algorithmic_bytes": float(algorithmic) if algorithmic else None,
+                     "algorithmic_bytes": alg,
                      "launch": note, "source": path})
     with open(out, "w") as f:
         json.dump(recs, f, indent=1)
