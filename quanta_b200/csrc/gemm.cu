@@ -444,6 +444,11 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         nf4_pairs[b] = AT::pack(kGemmNf4Levels[b & 15], kGemmNf4Levels[b >> 4]);
     }
 
+    // Programmatic dependent launch: the next kernel on the stream may start its prologue while this grid is in
+    // its tail; symmetrically this grid may have started during the previous kernel's tail, so everything that
+    // depends on that kernel — the activation loads, bias, every global write — sits behind griddepcontrol.wait.
+    // The weight stream (codes, scales, zero-points) does not and starts at once.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // Each producer initialises its own ring, checks in at the CTA-wide barrier without waiting
     // (barrier.arrive) and starts streaming at once; everybody else sees all barriers after
     // barrier.sync.  Producer loops are warp-uniform with one elected lane issuing, so the TMA
@@ -500,6 +505,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (CG == 2) { cluster_arrive(); cluster_wait(); }   // the peer's barriers must exist before the first load
         else asm volatile("barrier.arrive 2, %0;" ::"n"(kGemmThreads) : "memory");
         const uint64_t pol_x = policy_evict_last();          // activations are re-read by every CTA
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // x may be the previous kernel's output
         int slot = 0, issued = 0;
         uint32_t ph = 0;
         while (walk.next(tile, s0, s1)) {
@@ -603,6 +609,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     } else if (warp >= kFirstEpiWarp && warp < kFirstDqWarp) {
         // ===== epilogue: TMEM lane = output feature =====
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // bias reads, y / partial / counter writes
         const int quarter = warp & 3;
         const int row = 32 * quarter + lane;
         const int etid = tid - 32 * kFirstEpiWarp;
@@ -883,6 +890,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (warp >= kFirstEpiWarp && p.mb >= 64) {
         // epilogue + dequant warps: a pending last-segment fix-up is reduced by all of them (small
         // batches have too few rows to share: the epilogue warps did it in their loop)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("bar.sync 3, %0;" ::"n"(32 * (kEpiWarps + kDqWarps)) : "memory");
         const int ft = *reinterpret_cast<volatile int*>(&fin_tile);
         if (ft >= 0)
@@ -1027,11 +1035,20 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (env_int("QUANTA_B200_GEMM_PDL", 1)) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CG == 2 ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_x, tmap_s, tmap_z, outs, scale, zp, bias, counters, partial, p);
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
