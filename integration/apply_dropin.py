@@ -14,7 +14,7 @@ creates ``<output dir>/Quanta`` = the reference package plus
      CUDA tests (Quanta/tests/test_quantization.py:34-124) call them directly.
 
 Nothing else is touched; CPU tensors take the reference's own code, byte for byte.  Used by
-tests/test_gpu_reference_dropin.py; the input is never modified.
+tests/test_reference_dropin.py; the input is never modified.
 """
 import os
 import re

@@ -1081,6 +1081,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     const int mb_step = 16 * cg;                             // each CTA of a pair holds mb / 2 rows, a multiple of 16
     int mb = (int)((M + mb_step - 1) / mb_step * mb_step);
     if (mb > 256) mb = 256;
+    { const int cap = env_int("QUANTA_B200_GEMM_MB", 0); if (cap >= 16 && cap % 16 == 0 && mb > cap) mb = cap; }
     p.mb = mb;
     p.m_tiles = (int)((M + mb - 1) / mb);
     p.n_tiles = (n_tiles + cg - 1) / cg;
