@@ -59,6 +59,22 @@ constexpr int kSmStartWindow = 3;          // stages requested before the first 
 constexpr int kSmMaxOut = 8;
 constexpr int kSmCounterBytes = 64 * 1024; // same workspace header as gemm.cu (zero before, zero after)
 
+// The experiment switches cost ~25 instructions per unit in the consumers' loop: compiled in only on request.
+#ifdef QUANTA_SMALL_DBG
+#define SM_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define SM_DBG(p, bit) false
+#endif
+
+// Timeline of one launch (-DQUANTA_SMALL_TRACE build only): per CTA 40 clock64 stamps relative to kernel entry, + globaltimer at
+// entry / exit in slots 38 / 39.  Read back with quanta_debug_small_trace().
+#ifdef QUANTA_SMALL_TRACE
+__device__ long long g_sm_trace[kNumSMs][40];
+#define SM_TRACE(slot) do { if ((slot) < 38) g_sm_trace[blockIdx.x][(slot)] = clock64() - t_entry; } while (0)
+#else
+#define SM_TRACE(slot) do { } while (0)
+#endif
+
 struct SmallParams {
     int M, N, K;
     int S;                  // 256-K steps per row tile
@@ -69,7 +85,9 @@ struct SmallParams {
     int R;                  // weight ring stages
     int ldy, col0, n_out;
     int vec_y;              // 8-byte y stores are aligned in every output buffer
-    int dbg;                // experiment switches (QUANTA_B200_SMALL_DBG): 1 no compute, 2 no x staging, 4 no epilogue
+    int dbg;                // experiment switches (QUANTA_B200_SMALL_DBG; only in a -DQUANTA_SMALL_DBG build): 1 no compute,
+                            // 2 no x staging, 4 no epilogue, 8 no TMA
+    uint32_t mul4, mul12;   // 2^28, 2^20: `w >> 4` / `w >> 12` as IMAD.HI on the FMA pipe (see sm_shr)
     uint32_t stage_bytes;   // codes + scale tile + zero-point tile + raw activations [m_pad x 256]
     uint32_t code_bytes;
     uint32_t x_off;         // x ring
@@ -311,6 +329,10 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     auto xfull_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + s) * 8u; };
     auto xempty_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + kSmXRing + s) * 8u; };
 
+#ifdef QUANTA_SMALL_TRACE
+    const long long t_entry = clock64();
+    if (tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); g_sm_trace[blockIdx.x][38] = (long long)g; }
+#endif
     const unsigned int cta = blockIdx.x;
     const unsigned int u0 = p.U * cta / (unsigned int)p.G, u1 = p.U * (cta + 1u) / (unsigned int)p.G;
     const int n_units = (int)(u1 - u0);
@@ -324,12 +346,14 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // The producer initialises the weight ring itself, checks in at the CTA barrier WITHOUT waiting (bar.arrive)
     // and starts streaming at once; everybody else sees all barriers after bar.sync.
     if (tid == 32 * kSmConsWarps) {
+        SM_TRACE(32);
         prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z); prefetch_tensormap(&tmap_x);
         for (int s = 0; s < p.R; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar(s)), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar(s)), "r"(kSmConsWarps + kSmXWarps));
         }
         fence_barrier_init();
+        SM_TRACE(33);
     }
     if (tid == 0) {
         for (int s = 0; s < kSmXRing; ++s) {
@@ -348,6 +372,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (warp == kSmConsWarps) {
         // ===== producer: keeps the ring full across tile boundaries =====
         if (lane == 0) {
+            SM_TRACE(34);
             const uint64_t pol = policy_evict_first();       // weights are streamed once
             const uint64_t pol_x = policy_evict_last();      // activations are re-read by every row tile
             int slot = 0, i = 0;
@@ -378,11 +403,14 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             };
             while (walk.next(tile, s0, s1, final_seg)) {
                 for (int step = s0; step < s1; ++step, ++i) {
-                    if (p.dbg & 8) break;
+                    if (SM_DBG(p, 8)) break;
+                    if (i == 0) SM_TRACE(1);
                     if (i == kSmStartWindow) {
                         // start-up window (see the header): open the whole ring once the first stage has landed
                         dependency_wait();
+                        SM_TRACE(2);
                         sm_bar_wait(full_bar(0), 0u);
+                        SM_TRACE(3);
                     }
                     if (i >= p.R) sm_bar_wait(empty_bar(slot), ph ^ 1u);
                     const uint32_t bar = full_bar(slot);
@@ -394,6 +422,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
             }
             if (!waited) dependency_wait();
+            SM_TRACE(4);
         }
         return;
     }
@@ -405,7 +434,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // ===== publisher: releases the partial of every contributor segment that is not the CTA's last one while
         //       the stream runs on (a segment that reaches the tile's last step makes this CTA the reducer: no release) =====
         while (walk.next(tile, s0, s1, final_seg)) {
-            if (final_seg || s1 == S || (p.dbg & 4)) continue;
+            if (final_seg || s1 == S || SM_DBG(p, 4)) continue;
             asm volatile("bar.sync 2, 160;" ::: "memory");   // the 4 output warps have stored the partial
             if (lane == 0) sm_contribute(counters, tile);
         }
@@ -431,7 +460,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             xdst[it] = (uint32_t)((((nb * 4 + blk) * 2 + j) * 32 + g * 4 + t) * 16);
             xsum_dst[it] = (uint32_t)(NB * 4096 + ((nb * 4 + blk) * 8 + g) * 4);
         }
-        const bool x_on = !(p.dbg & 2), w_on = !(p.dbg & 8);
+        const bool x_on = !SM_DBG(p, 2), w_on = !SM_DBG(p, 8);
         int xs = 0, ws_ = 0;
         uint32_t ph = 0, wph_ = 0;
         for (int i = 0; i < n_units; ++i) {
@@ -492,7 +521,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) { rows[sl][0] = (2 * rg + sl) * 16 + sm_row_of<BITS>(gid); rows[sl][1] = rows[sl][0] + 8; }
 
-    const bool do_compute = !(p.dbg & 1), do_x = !(p.dbg & 2), do_epi = !(p.dbg & 4), do_wait = !(p.dbg & 8);
+    const bool do_compute = !SM_DBG(p, 1), do_x = !SM_DBG(p, 2), do_epi = !SM_DBG(p, 4), do_wait = !SM_DBG(p, 8);
     // Per-thread shared-memory offsets (the block b = kq is fixed per warp; rows + 8 / + 16 keep the swizzle
     // phase, so every other address of a unit is one of these plus an immediate).
     const int r00 = rows[0][0];
@@ -502,6 +531,12 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t s_off = p.code_bytes + (uint32_t)r00 * 16u + (uint32_t)kq * 4u;
     const uint32_t xb_off = p.x_off + (uint32_t)((kq * 2) * 512 + lane * 16);
     const uint32_t xs_off = p.x_off + (uint32_t)(NB * 4096 + (kq * 8 + 2 * tig) * 4);
+    // Absolute shared-memory addresses of this thread's words in slot 0.  Made opaque so that they live in
+    // registers: ptxas otherwise rematerialises the whole lane / warp arithmetic above inside the unit loop
+    // (~30 of its ~160 instructions).
+    uint32_t w_base = smem + w_off, s_base = smem + s_off, xb_base = smem + xb_off, xs_base0 = smem + xs_off;
+    asm volatile("" : "+r"(w_base), "+r"(s_base), "+r"(xb_base), "+r"(xs_base0));
+    const uint32_t stage_bytes = p.stage_bytes, x_slot_bytes = p.x_slot_bytes;
 
     float tot[2][NB][4];
 #pragma unroll
@@ -511,14 +546,20 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     int wslot = 0, xs_cur = 0, red_tile = -1;
     uint32_t wph = 0, xph = 0;
 
+#ifdef QUANTA_SMALL_TRACE
+    int tr_unit = 0;
+#endif
+    if (tid == 0) SM_TRACE(5);
     while (walk.next(tile, s0, s1, final_seg)) {
         for (int step = s0; step < s1; ++step) {
-            if (do_wait) sm_bar_wait(full_bar(wslot), wph);
+            // The staging warps signal xfull only after they have seen the stage's `full` barrier complete (all of
+            // its TMA bytes are in shared memory by then), so one wait covers weights and activations.
             if (do_x) sm_bar_wait(xfull_bar(xs_cur), xph);
+            else if (do_wait) sm_bar_wait(full_bar(wslot), wph);
 
             if (do_compute) {
-                const uint32_t sb = smem + (uint32_t)wslot * p.stage_bytes;
-                const uint32_t xs_base = smem + (uint32_t)xs_cur * p.x_slot_bytes;
+                const uint32_t w_cur = w_base + (uint32_t)wslot * stage_bytes, s_cur = s_base + (uint32_t)wslot * stage_bytes;
+                const uint32_t xb_cur = xb_base + (uint32_t)xs_cur * x_slot_bytes, xs_addr = xs_base0 + (uint32_t)xs_cur * x_slot_bytes;
                 // ---- every shared-memory read of the unit goes out first (they are ordered asm statements;
                 //      the arithmetic below is free for the compiler to interleave) ----
                 uint32_t wraw[2][2][BITS == 4 ? 2 : 4];      // [slab][row half][words]
@@ -526,7 +567,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t wa = sb + w_off + (uint32_t)(sl * 2048 + h * 1024);
+                        const uint32_t wa = w_cur + (uint32_t)(sl * 2048 + h * 1024);
                         if (BITS == 4) {
                             const uint2 w = sm_lds64(wa);
                             wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y;
@@ -539,9 +580,9 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 uint2 xs2[NB];
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
-                    xb[nb][0] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096));
-                    xb[nb][1] = sm_lds128(xs_base + xb_off + (uint32_t)(nb * 4096 + 512));
-                    xs2[nb] = sm_lds64(xs_base + xs_off + (uint32_t)(nb * 128));
+                    xb[nb][0] = sm_lds128(xb_cur + (uint32_t)(nb * 4096));
+                    xb[nb][1] = sm_lds128(xb_cur + (uint32_t)(nb * 4096 + 512));
+                    xs2[nb] = sm_lds64(xs_addr + (uint32_t)(nb * 128));
                 }
                 float sc[2][2], zc[2][2];
                 const float off = BITS == 4 ? T::kOffset : 0.0f;
@@ -549,8 +590,8 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        sc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128));
-                        zc[sl][h] = sm_lds32(sb + s_off + (uint32_t)(sl * 256 + h * 128 + 2048));
+                        sc[sl][h] = sm_lds32(s_cur + (uint32_t)(sl * 256 + h * 128));
+                        zc[sl][h] = sm_lds32(s_cur + (uint32_t)(sl * 256 + h * 128 + 2048));
                     }
                 // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
                 //      are independent (2 slabs x NB accumulators) ----
@@ -566,11 +607,15 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     for (int sl = 0; sl < 2; ++sl) {
                         if (BITS == 4) {
                             // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k
-                            const uint32_t w0 = wraw[sl][0][k >> 1] >> (8 * (k & 1)), w1 = wraw[sl][1][k >> 1] >> (8 * (k & 1));
+                            // the shifts by 4 and 12 are multiplications (IMAD.HI by 2^28 / 2^20 from the parameter bank,
+                            // opaque to ptxas): they issue on the FMA pipe while the LOP3s keep the ALU pipe busy
+                            const uint32_t r0 = wraw[sl][0][k >> 1], r1 = wraw[sl][1][k >> 1];
+                            const uint32_t w0 = (k & 1) ? (r0 >> 8) : r0, w1 = (k & 1) ? (r1 >> 8) : r1;
+                            const uint32_t m = (k & 1) ? p.mul12 : p.mul4;
                             a[sl][0] = sm_and_or(w0, 0x000F000Fu, T::kMagic);
                             a[sl][1] = sm_and_or(w1, 0x000F000Fu, T::kMagic);
-                            a[sl][2] = sm_and_or(w0 >> 4, 0x000F000Fu, T::kMagic);
-                            a[sl][3] = sm_and_or(w1 >> 4, 0x000F000Fu, T::kMagic);
+                            a[sl][2] = sm_and_or(__umulhi(r0, m), 0x000F000Fu, T::kMagic);
+                            a[sl][3] = sm_and_or(__umulhi(r1, m), 0x000F000Fu, T::kMagic);
                         } else {
                             uint32_t p0[2], p1[2];
                             sm_pairs8<ACT>(wraw[sl][0][k], p0); sm_pairs8<ACT>(wraw[sl][1][k], p1);
@@ -603,7 +648,11 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             if (lane == 0) { sm_bar_arrive(empty_bar(wslot)); if (do_x) sm_bar_arrive(xempty_bar(xs_cur)); }
             if (++wslot == p.R) { wslot = 0; wph ^= 1u; }
             if (++xs_cur == kSmXRing) { xs_cur = 0; xph ^= 1u; }
+#ifdef QUANTA_SMALL_TRACE
+            if (tid == 0 && tr_unit < 24) { SM_TRACE(8 + tr_unit); ++tr_unit; }
+#endif
         }
+        if (tid == 0) SM_TRACE(6);
         if (do_epi) {
             // ===== end of this CTA's segment [s0, s1) of `tile`: the 4 K quarters meet in shared memory =====
             const bool whole = s0 == 0 && s1 == S;
@@ -679,15 +728,29 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             if (!whole && final_seg && s1 != S && tid == 0) sm_contribute(counters, tile);
         }
     }
+    if (tid == 0) SM_TRACE(7);
     if (red_tile >= 0 && do_epi) {
         // ===== reducer duty: the other contributors' partials (lower CTA indices) =====
         const unsigned int tu0 = (unsigned int)red_tile * (unsigned int)S;
         const int c_first = sm_cta_of_unit(tu0, p), c_last = (int)cta;
         if (tid == 0) sm_await_contributors(counters, red_tile, c_last - c_first);
         sm_cons_sync();
+        if (tid == 0) SM_TRACE(36);
         sm_fixup<ACT>(p, bias, partial, red_tile, c_first, c_last, tid, kSmConsThreads);
     }
+#ifdef QUANTA_SMALL_TRACE
+    if (tid == 0) {
+        SM_TRACE(37);
+        unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); g_sm_trace[blockIdx.x][39] = (long long)g;
+    }
+#endif
 }
+
+#ifdef QUANTA_SMALL_TRACE
+extern "C" __attribute__((visibility("default"))) int quanta_debug_small_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_sm_trace, sizeof(long long) * kNumSMs * 40);
+}
+#endif
 
 // ---- host side --------------------------------------------------------------
 
@@ -759,6 +822,8 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     const int smem = (int)(p.bar_off + bar_bytes);
     p.ldy = (int)ldy; p.col0 = (int)col0; p.n_out = n_out;
     p.dbg = small_tuning().dbg;
+    p.mul4 = 1u << 28;
+    p.mul12 = 1u << 20;
     bool aligned8 = true;
     for (int o = 0; o < kSmMaxOut; ++o) {
         p.y[o] = o < n_out ? ys[o] : nullptr;

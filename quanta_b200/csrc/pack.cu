@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // 16 codes (uint4) -> 8 bytes (uint2) per vector.
 template <bool HI>
 __global__ void __launch_bounds__(256) pack4_vec_kernel(const uint4* __restrict__ q, int64_t nvec, uint2* __restrict__ out) {
-    pdl_enter();
+    pdl_wait(); 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto pack = [](uint4 v) {
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) pack4_tail_kernel(const uint8_t* __restri
 // 8 packed bytes (uint2) -> 16 codes (uint4) per vector.
 template <bool HI>
 __global__ void __launch_bounds__(256) unpack4_vec_kernel(const uint2* __restrict__ p, int64_t nvec, uint4* __restrict__ out) {
-    pdl_enter();
+    pdl_wait(); 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     auto unpack = [](uint2 v) {

@@ -397,7 +397,7 @@ quantize_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_row
         fence_barrier_init();
     }
     __syncthreads();
-    pdl_enter();                                           // the set-up above may overlap the previous kernel's tail
+    pdl_wait();                                            // the set-up above may overlap the previous kernel's tail
 
     if (warp == kConsumerWarps) {
         // ===== producer warp: one lane streams tiles into the ring =====
@@ -1273,7 +1273,7 @@ quantize_rows_tma_multi_kernel(const __grid_constant__ MultiArgs a, int log2_lan
         fence_barrier_init();
     }
     __syncthreads();
-    pdl_enter();                                           // the set-up above may overlap the previous kernel's tail
+    pdl_wait();                                            // the set-up above may overlap the previous kernel's tail
 
     if (warp == kConsumerWarps) {
         if (lane == 0) {
