@@ -44,6 +44,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace quanta {
 
@@ -52,12 +53,24 @@ constexpr int kSmConsWarps = 16;           // warp w: rows 32 (w & 3) .. +32, bl
 constexpr int kSmConsThreads = 32 * kSmConsWarps;
 constexpr int kSmXWarps = 4;               // activation staging warps
 constexpr int kSmThreads = kSmConsThreads + 64 + 32 * kSmXWarps;   // + producer warp + publisher warp + staging warps
-constexpr int kSmStepK = 256;              // K per stage
+constexpr int kSmKGran = 256;              // K must be a multiple of this (16-byte scale rows; a partial last step is zero-filled)
 constexpr int kSmMaxRing = 8;
-constexpr int kSmXRing = 4;                // activation slots (one 256-K unit each)
-constexpr int kSmStartWindow = 3;          // stages requested before the first one has landed
+constexpr int kSmMaxXRing = 4;             // activation slots (one stage each)
+constexpr int kSmStartWindow = 2;          // default number of stages requested before the first one has landed
 constexpr int kSmMaxOut = 8;
 constexpr int kSmCounterBytes = 64 * 1024; // same workspace header as gemm.cu (zero before, zero after)
+
+// One stage = 256 BYTES of codes per weight row (two SWIZZLE_128B boxes of [128 rows x 128 B]): HBM serves 256-byte
+// row pieces at its full rate, 128-byte ones (the 4-bit kernel's first form: 256 K per stage) at ~75 % of it
+// (measured: 4.8 vs 6.7 TB/s in the steady state of this kernel).
+template <int BITS> struct SmGeom {
+    static constexpr int kStepK = 2048 / BITS;                       // K values per stage: 512 (4-bit) / 256 (8-bit)
+    static constexpr int kBlk = kStepK / 64;                         // 64-K blocks per stage: 8 / 4
+    static constexpr int kBpw = kBlk / 4;                            // blocks per consumer warp and stage: 2 / 1
+    static constexpr uint32_t kCodeBytes = 32768u;
+    static constexpr uint32_t kParamTile = (uint32_t)(kSmRows * kBlk * 4);   // one [128 rows x kBlk] fp32 tile
+    static constexpr uint32_t kStageBytes = kCodeBytes + 2u * kParamTile;    // codes | scales | zero-points
+};
 
 // The experiment switches cost ~25 instructions per unit in the consumers' loop: compiled in only on request.
 #ifdef QUANTA_SMALL_DBG
@@ -77,21 +90,22 @@ __device__ long long g_sm_trace[kNumSMs][40];
 
 struct SmallParams {
     int M, N, K;
-    int S;                  // 256-K steps per row tile
+    int S;                  // stages (SmGeom::kStepK K values) per row tile; the last one may be partial
     int n_tiles;
     int G;                  // CTAs
     unsigned int U;         // units = n_tiles * S
+    unsigned int q, r;      // U / G, U % G: CTA c owns units [c q + min(c, r), + q + (c < r))
+    unsigned int s_magic;   // ceil(2^32 / S): u / S == __umulhi(u, s_magic) for every u <= U (gemm_small_eligible); 0: S == 1
     int m_pad;              // 8 * NB
     int R;                  // weight ring stages
+    int XR;                 // activation ring slots (<= kSmMaxXRing)
+    int window;             // stages requested before the first one has landed
     int ldy, col0, n_out;
     int vec_y;              // 8-byte y stores are aligned in every output buffer
     int dbg;                // experiment switches (QUANTA_B200_SMALL_DBG; only in a -DQUANTA_SMALL_DBG build): 1 no compute,
                             // 2 no x staging, 4 no epilogue, 8 no TMA
-    uint32_t mul4, mul12;   // 2^28, 2^20: `w >> 4` / `w >> 12` as IMAD.HI on the FMA pipe (see sm_shr)
-    uint32_t stage_bytes;   // codes + scale tile + zero-point tile + raw activations [m_pad x 256]
-    uint32_t code_bytes;
     uint32_t x_off;         // x ring
-    uint32_t x_slot_bytes;  // m_pad * 512 (chunks) + NB * 128 (block sums)
+    uint32_t x_slot_bytes;  // NB * kBlk * (1024 fragment bytes + 32 block-sum bytes)
     uint32_t red_off;       // [3][4 row groups][2 slabs][NB][4][32] floats: the K quarters of a tile meet here
     uint32_t bar_off;       // mbarriers + flags
     void* y[kSmMaxOut];
@@ -202,13 +216,16 @@ template <int BITS> __device__ __forceinline__ int sm_row_of(int gid) {
     return BITS == 4 ? (((gid & 3) << 1) | (gid >> 2)) : (((gid & 1) << 2) | (gid >> 1));
 }
 
-// CTA whose unit range [U c / G, U (c+1) / G) contains unit u
+// The unit range of CTA c, and the CTA whose range contains unit u.  No division on the prologue's path: a 32-bit
+// division is ~100 instructions and every CTA's first TMA request waits for it.
+__device__ __forceinline__ unsigned int sm_first_unit(unsigned int c, const SmallParams& p) {
+    return c * p.q + (c < p.r ? c : p.r);
+}
+__device__ __forceinline__ unsigned int sm_div_magic(unsigned int u, unsigned int magic) { return magic ? __umulhi(u, magic) : u; }
+__device__ __forceinline__ unsigned int sm_div_S(unsigned int u, const SmallParams& p) { return sm_div_magic(u, p.s_magic); }
 __device__ __forceinline__ int sm_cta_of_unit(unsigned int u, const SmallParams& p) {
-    const unsigned int G = (unsigned int)p.G;
-    unsigned int c = (unsigned int)(((unsigned long long)u * G) / p.U);
-    while (c + 1 < G && p.U * (c + 1) / G <= u) ++c;
-    while (c > 0 && p.U * c / G > u) --c;
-    return (int)c;
+    const unsigned int big = p.r * (p.q + 1u);
+    return (int)(u < big ? u / (p.q + 1u) : p.r + (u - big) / p.q);
 }
 
 // The segments of a CTA's unit range [u0, u1) — a segment = this CTA's steps [s0, s1) of one row tile — in
@@ -217,11 +234,11 @@ __device__ __forceinline__ int sm_cta_of_unit(unsigned int u, const SmallParams&
 // (the tail of the first tile, the head of the last one) are processed FIRST and handed over while the stream
 // runs on, and the kernel ends on a whole tile.  With no whole tile in the range the natural order is kept.
 struct SmWalk {
-    unsigned int rb[3], re[3], u, S;
+    unsigned int rb[3], re[3], u, S, magic;
     int nr, r;
-    __device__ __forceinline__ void init(unsigned int u0, unsigned int u1, unsigned int S_) {
-        S = S_; r = 0; nr = 0;
-        const unsigned int t0 = u0 / S, tl = (u1 - 1u) / S;
+    __device__ __forceinline__ void init(unsigned int u0, unsigned int u1, unsigned int S_, unsigned int magic_) {
+        S = S_; magic = magic_; r = 0; nr = 0;
+        const unsigned int t0 = sm_div_magic(u0, magic), tl = sm_div_magic(u1 - 1u, magic);
         const bool f_part = (u0 - t0 * S) != 0u && t0 != tl;            // tail of the first tile
         const bool l_part = (u1 - tl * S) != S && t0 != tl;             // head of the last tile
         const unsigned int wb = f_part ? (t0 + 1u) * S : u0, we = l_part ? tl * S : u1;
@@ -238,7 +255,7 @@ struct SmWalk {
     __device__ __forceinline__ bool next(int& tile, int& s0, int& s1, bool& final) {
         if (r < nr && u >= re[r]) { ++r; if (r < nr) u = rb[r]; }
         if (r >= nr) return false;
-        const unsigned int t = u / S, b = u - t * S, left = re[r] - u;
+        const unsigned int t = sm_div_magic(u, magic), b = u - t * S, left = re[r] - u;
         tile = (int)t; s0 = (int)b;
         s1 = (left < S - b) ? (int)(b + left) : (int)S;
         u += (unsigned int)(s1 - s0);
@@ -273,7 +290,6 @@ template <typename ACT>
 __device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __restrict__ bias, const float* __restrict__ partial,
                                          int tile, int c_first, int c_last, int j, int nthreads) {
     using T = SmTraits<ACT>;
-    const unsigned int S = (unsigned int)p.S;
     const int n0 = tile * kSmRows;
     const int f4 = 4 * (j & 31), gn4 = n0 + f4;
     const size_t slot = (size_t)(kSmRows * p.m_pad);
@@ -289,7 +305,7 @@ __device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __rest
                 const int c = c0 + u;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (c <= c_last) {
-                    const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / S)) ? 0 : 1;
+                    const int wc = (tile == (int)sm_div_S(sm_first_unit((unsigned int)c, p), p)) ? 0 : 1;
                     v[u] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)c * 2 + wc) * slot + m * kSmRows + f4));
                 }
             }
@@ -315,9 +331,10 @@ __device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __rest
 template <typename ACT, int BITS, int NB>
 __global__ void __launch_bounds__(kSmThreads, 1)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
-                  const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_x, const ACT* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tmap_z, const ACT* __restrict__ x, const ACT* __restrict__ bias,
                   unsigned int* __restrict__ counters, float* __restrict__ partial, const __grid_constant__ SmallParams p) {
     using T = SmTraits<ACT>;
+    using G = SmGeom<BITS>;
     extern __shared__ __align__(1024) uint8_t sm_raw[];
 
     const uint32_t smem = smem_u32(sm_raw);
@@ -327,19 +344,18 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
     auto empty_bar = [&](int s) { return bars + (uint32_t)(kSmMaxRing + s) * 8u; };
     auto xfull_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + s) * 8u; };
-    auto xempty_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + kSmXRing + s) * 8u; };
+    auto xempty_bar = [&](int s) { return bars + (uint32_t)(2 * kSmMaxRing + kSmMaxXRing + s) * 8u; };
 
 #ifdef QUANTA_SMALL_TRACE
     const long long t_entry = clock64();
     if (tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); g_sm_trace[blockIdx.x][38] = (long long)g; }
 #endif
     const unsigned int cta = blockIdx.x;
-    const unsigned int u0 = p.U * cta / (unsigned int)p.G, u1 = p.U * (cta + 1u) / (unsigned int)p.G;
-    const int n_units = (int)(u1 - u0);
+    const unsigned int u0 = sm_first_unit(cta, p), u1 = sm_first_unit(cta + 1u, p);
     const int S = p.S;
-    const int tile0 = (int)(u0 / (unsigned int)S);       // the first tile of the range owns partial slot 0
+    const int tile0 = (int)sm_div_S(u0, p);              // the first tile of the range owns partial slot 0
     SmWalk walk;
-    walk.init(u0, u1, (unsigned int)S);
+    walk.init(u0, u1, (unsigned int)S, p.s_magic);
     int tile, s0, s1;
     bool final_seg;
 
@@ -347,16 +363,16 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // and starts streaming at once; everybody else sees all barriers after bar.sync.
     if (tid == 32 * kSmConsWarps) {
         SM_TRACE(32);
-        prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z); prefetch_tensormap(&tmap_x);
+        prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_s); prefetch_tensormap(&tmap_z);
         for (int s = 0; s < p.R; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar(s)), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar(s)), "r"(kSmConsWarps + kSmXWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar(s)), "r"(kSmConsWarps));
         }
         fence_barrier_init();
         SM_TRACE(33);
     }
     if (tid == 0) {
-        for (int s = 0; s < kSmXRing; ++s) {
+        for (int s = 0; s < kSmMaxXRing; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xfull_bar(s)), "r"(kSmXWarps));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xempty_bar(s)), "r"(kSmConsWarps));
         }
@@ -371,66 +387,50 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
     if (warp == kSmConsWarps) {
         // ===== producer: keeps the ring full across tile boundaries =====
+        // Programmatic dependent launch: this grid may start while the previous kernel on the stream is still in its
+        // tail.  The producer touches only the weight operands, which do not depend on that kernel (common.cuh,
+        // pdl_wait), so it never waits for it; the activations and every global write of this grid are ordered
+        // behind griddepcontrol.wait in the other warps.
         if (lane == 0) {
             SM_TRACE(34);
             const uint64_t pol = policy_evict_first();       // weights are streamed once
-            const uint64_t pol_x = policy_evict_last();      // activations are re-read by every row tile
             int slot = 0, i = 0;
             uint32_t ph = 0;
-            // Programmatic dependent launch: this grid may start while the previous kernel on the stream is still in
-            // its tail.  The weights do not depend on it, so the first stages' codes / scales / zero-points are
-            // requested at once; the activations (the previous kernel's output, in a chain of layers) and every
-            // global write of this kernel wait for griddepcontrol.wait — a no-op in an ordinary launch.
-            int pend_step[kSmStartWindow], npend = 0;
-            bool waited = false;
-            auto issue_weights = [&](uint32_t bar, uint32_t dst, int kb, int n0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.stage_bytes) : "memory");
-                if (BITS == 4) {
-                    sm_tma_2d(dst, &tmap_w, bar, kb / 2, n0, pol);
-                } else {
-                    sm_tma_2d(dst, &tmap_w, bar, kb, n0, pol);
-                    sm_tma_2d(dst + 16384u, &tmap_w, bar, kb + 128, n0, pol);
-                }
-                sm_tma_2d(dst + p.code_bytes, &tmap_s, bar, kb / 64, n0, pol);
-                sm_tma_2d(dst + p.code_bytes + 2048u, &tmap_z, bar, kb / 64, n0, pol);
-            };
-            auto dependency_wait = [&]() {
-                asm volatile("griddepcontrol.wait;" ::: "memory");
-                waited = true;
-                // the activations [m_pad rows x 256 K] of the stages requested so far (rows past M arrive zero-filled)
-                for (int k = 0; k < npend; ++k)
-                    sm_tma_2d(smem + (uint32_t)k * p.stage_bytes + p.code_bytes + 4096u, &tmap_x, full_bar(k), pend_step[k] * kSmStepK, 0, pol_x);
-            };
             while (walk.next(tile, s0, s1, final_seg)) {
                 for (int step = s0; step < s1; ++step, ++i) {
                     if (SM_DBG(p, 8)) break;
                     if (i == 0) SM_TRACE(1);
-                    if (i == kSmStartWindow) {
-                        // start-up window (see the header): open the whole ring once the first stage has landed
-                        dependency_wait();
+                    if (i == p.window) {
+                        // start-up window: the TMA unit works on all of its outstanding copies at once, so the first
+                        // stage lands sooner when only a few are requested; the whole ring opens once it is there
                         SM_TRACE(2);
                         sm_bar_wait(full_bar(0), 0u);
                         SM_TRACE(3);
                     }
                     if (i >= p.R) sm_bar_wait(empty_bar(slot), ph ^ 1u);
                     const uint32_t bar = full_bar(slot);
-                    const uint32_t dst = smem + (uint32_t)slot * p.stage_bytes;
-                    issue_weights(bar, dst, step * kSmStepK, tile * kSmRows);
-                    if (waited) sm_tma_2d(dst + p.code_bytes + 4096u, &tmap_x, bar, step * kSmStepK, 0, pol_x);
-                    else pend_step[npend++] = step;
+                    const uint32_t dst = smem + (uint32_t)slot * G::kStageBytes;
+                    const int kb = step * G::kStepK, n0 = tile * kSmRows;
+                    const int cb = kb * BITS / 8;            // byte column of the stage in a code row
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G::kStageBytes) : "memory");
+                    sm_tma_2d(dst, &tmap_w, bar, cb, n0, pol);
+                    sm_tma_2d(dst + 16384u, &tmap_w, bar, cb + 128, n0, pol);
+                    sm_tma_2d(dst + G::kCodeBytes, &tmap_s, bar, kb / 64, n0, pol);
+                    sm_tma_2d(dst + G::kCodeBytes + G::kParamTile, &tmap_z, bar, kb / 64, n0, pol);
                     if (++slot == p.R) { slot = 0; ph ^= 1u; }
                 }
             }
-            if (!waited) dependency_wait();
             SM_TRACE(4);
         }
         return;
     }
     // Let the next kernel on the stream start its own prologue as soon as this grid's CTAs make room (its weights do
-    // not depend on us); every other warp orders its global accesses behind the previous kernel.
+    // not depend on us).  Every warp orders its GLOBAL accesses behind the previous kernel (griddepcontrol.wait): the
+    // staging warps before they read x, the publisher before its first release, the consumers — which read shared
+    // memory only — before the first store of a segment's result.  Their set-up runs ahead of the wait.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp == kSmConsWarps + 1) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         // ===== publisher: releases the partial of every contributor segment that is not the CTA's last one while
         //       the stream runs on (a segment that reaches the tile's last step makes this CTA the reducer: no release) =====
         while (walk.next(tile, s0, s1, final_seg)) {
@@ -443,100 +443,140 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
     if (warp >= kSmConsWarps + 2) {
         // ===== activation staging warps =====
-        // The unit's activations arrive with its weights (raw [m_pad x 256] rows behind the zero-point tile).  Chunk c
-        // (c = 32 xw + lane + 128 it): batch row m = c / 32, block (c / 8) & 3, 8 consecutive K values 8 (c & 7) of the
-        // block -> slot chunk (((nb 4 + blk) 2 + j) 32 + gid 4 + tig) with nb = m / 8, gid = m & 7, tig = (c & 7) / 2,
-        // j = c & 1: a consumer warp's B-fragment read of one (nb, blk, j) is 512 contiguous bytes.
-        constexpr int kChunks = 8 * NB * 32;                 // 16-byte x chunks per unit
-        constexpr int kPer = kChunks / (32 * kSmXWarps);
+        // They read the stage's activations x[0..m_pad) x [kStepK] straight from global memory (L2: every CTA reads the
+        // same few hundred KB), one stage ahead in registers, and write them in MMA fragment order plus the per-block
+        // sums of x into a ring of their own.  Chunk c (c = 32 xw + lane + 128 it) = 8 consecutive K values: batch row
+        // m = c / kRowChunks, cc = c % kRowChunks -> block cc / 8, K offset 8 (cc & 7) within the block -> slot chunk
+        // (((nb kBlk + blk) 2 + j) 32 + gid 4 + tig) with nb = m / 8, gid = m & 7, tig = (cc & 7) / 2, j = cc & 1: a
+        // consumer warp's B-fragment read of one (nb, blk, j) is 512 contiguous bytes.
+        constexpr int kRowChunks = G::kStepK / 8;            // 16-byte chunks per batch row and stage: 64 / 32
+        constexpr int kChunks = 8 * NB * kRowChunks;
+        constexpr int kPer = kChunks / (32 * kSmXWarps);     // chunks per thread and stage: 4 NB / 2 NB
+        constexpr int kMStep = 32 * kSmXWarps / kRowChunks;  // batch rows between a thread's chunks: 2 / 4
         const int xw = warp - (kSmConsWarps + 2);
-        uint32_t xsrc[kPer], xdst[kPer], xsum_dst[kPer];
+        // chunk `it` of this thread: batch row m_first + kMStep it, always the same cc
+        const int c_first = 32 * xw + lane;
+        const int m_first = c_first / kRowChunks, cc = c_first % kRowChunks, blk = cc >> 3, c8 = cc & 7;
+        const uint32_t xdst0 = (uint32_t)(((blk * 2 + (c8 & 1)) * 32 + m_first * 4 + (c8 >> 1)) * 16);
+        const uint32_t xsum0 = (uint32_t)(NB * G::kBlk * 1024 + (blk * 8 + m_first) * 4);
+        const ACT* const xrow0 = x + (size_t)m_first * (size_t)p.K + cc * 8;
+        const size_t row_step = (size_t)kMStep * (size_t)p.K;
+        if (SM_DBG(p, 2)) return;
+        // Rows past M are zero in every slot, for ever: written once, here (ordered before the consumers' reads by the
+        // first xfull arrive of this thread).
+        for (uint32_t o = (uint32_t)(32 * xw + lane) * 16u; o < (uint32_t)p.XR * p.x_slot_bytes; o += 32u * kSmXWarps * 16u)
+            sm_sts128(smem + p.x_off + o, make_uint4(0u, 0u, 0u, 0u));
+        asm volatile("bar.sync 3, %0;" ::"n"(32 * kSmXWarps) : "memory");   // nobody's zeros land on a sibling's first unit
+        const int n_units = (int)(u1 - u0);
+        // RPT chunks per thread and unit are live (1 when M <= kMStep: then the thread's other chunks are padding rows),
+        // DEPTH units are in flight in registers: an L2 round trip under the weight stream's load is 2-3 K cycles, and
+        // right after the dependency wait — when up to R stages of weights are already waiting in shared memory — these
+        // warps, not the stream, pace the consumers.
+        auto stage_all = [&](auto rpt_tag, auto depth_tag) {
+            constexpr int RPT = decltype(rpt_tag)::value, DEPTH = decltype(depth_tag)::value;
+            uint4 buf[DEPTH][RPT];
+            SmWalk ahead = walk;
+            int a_tile, a_s0 = 0, a_s1 = 0, a_step = 0;
+            bool a_fin, a_ok = ahead.next(a_tile, a_s0, a_s1, a_fin);
+            a_step = a_s0;
+            auto fetch_next = [&](uint4* dst) {
+                if (!a_ok) return;
+                const int k = a_step * G::kStepK;
+                const bool k_ok = k + cc * 8 < p.K;          // false only in the K tail of a partial last stage
 #pragma unroll
-        for (int it = 0; it < kPer; ++it) {
-            const int c = 32 * xw + lane + 32 * kSmXWarps * it;
-            const int m = c >> 5, blk = (c >> 3) & 3, c8 = c & 7;
-            const int nb = m >> 3, g = m & 7, t = c8 >> 1, j = c8 & 1;
-            xsrc[it] = p.code_bytes + 4096u + (uint32_t)(c * 16);
-            xdst[it] = (uint32_t)((((nb * 4 + blk) * 2 + j) * 32 + g * 4 + t) * 16);
-            xsum_dst[it] = (uint32_t)(NB * 4096 + ((nb * 4 + blk) * 8 + g) * 4);
-        }
-        const bool x_on = !SM_DBG(p, 2), w_on = !SM_DBG(p, 8);
-        int xs = 0, ws_ = 0;
-        uint32_t ph = 0, wph_ = 0;
-        for (int i = 0; i < n_units; ++i) {
-            if (w_on) sm_bar_wait(full_bar(ws_), wph_);
-            if (!x_on) {                                     // experiment switch: release the stage, stage nothing
-                __syncwarp();
-                if (lane == 0) sm_bar_arrive(empty_bar(ws_));
-                if (++ws_ == p.R) { ws_ = 0; wph_ ^= 1u; }
-                continue;
-            }
-            if (i >= kSmXRing) sm_bar_wait(xempty_bar(xs), ph ^ 1u);
-            const uint32_t stage = smem + (uint32_t)ws_ * p.stage_bytes;
-            const uint32_t slot = smem + p.x_off + (uint32_t)xs * p.x_slot_bytes;
-            uint4 raw[kPer];
-#pragma unroll
-            for (int it = 0; it < kPer; ++it) raw[it] = sm_lds128(stage + xsrc[it]);
-#pragma unroll
-            for (int it = 0; it < kPer; ++it) {
-                uint4 v = raw[it];
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                float sum = 0.0f;
-                if (SmTraits<ACT>::kOffset == 128.0f) {
-                    // bf16 -> fp32 is a shift / mask
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) sum += __uint_as_float(w4[q] << 16) + __uint_as_float(w4[q] & 0xFFFF0000u);
-                } else {
-                    const ACT* e = reinterpret_cast<const ACT*>(&v);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) sum += T::to_float(e[q]);
+                for (int it = 0; it < RPT; ++it) {
+                    dst[it] = make_uint4(0u, 0u, 0u, 0u);    // rows past M and that tail read as zero
+                    if (k_ok && m_first + kMStep * it < p.M) dst[it] = __ldcg(reinterpret_cast<const uint4*>(xrow0 + it * row_step + k));
                 }
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-                if (BITS == 4) {
-                    uint4 o;
-                    o.x = sm_prmt(v.x, v.z, 0x5410u);        // (x0, x4)
-                    o.y = sm_prmt(v.x, v.z, 0x7632u);        // (x1, x5)
-                    o.z = sm_prmt(v.y, v.w, 0x5410u);        // (x2, x6)
-                    o.w = sm_prmt(v.y, v.w, 0x7632u);        // (x3, x7)
-                    v = o;
+                if (++a_step >= a_s1) { a_ok = ahead.next(a_tile, a_s0, a_s1, a_fin); a_step = a_s0; }
+            };
+            asm volatile("griddepcontrol.wait;" ::: "memory");   // x is the previous kernel's output
+            if (xw == 0 && lane == 0) SM_TRACE(24);
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) fetch_next(buf[d]);
+            int xs = 0, i = 0;
+            uint32_t ph = 0;
+            while (i < n_units) {
+#pragma unroll
+                for (int d = 0; d < DEPTH; ++d) {
+                    if (i >= n_units) break;
+                    if (i >= p.XR) sm_bar_wait(xempty_bar(xs), ph ^ 1u);
+                    const uint32_t slot = smem + p.x_off + (uint32_t)xs * p.x_slot_bytes;
+#pragma unroll
+                    for (int it = 0; it < RPT; ++it) {
+                        const int mo = kMStep * it;          // compile-time: nb = mo / 8, row within the block of 8: (mo & 7) + m_first
+                        uint4 v = buf[d][it];
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                        float sum = 0.0f;
+                        if (SmTraits<ACT>::kOffset == 128.0f) {
+                            // bf16 -> fp32 is a shift / mask
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) sum += __uint_as_float(w4[q] << 16) + __uint_as_float(w4[q] & 0xFFFF0000u);
+                        } else {
+                            const ACT* e = reinterpret_cast<const ACT*>(&v);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) sum += T::to_float(e[q]);
+                        }
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                        if (BITS == 4) {
+                            uint4 o;
+                            o.x = sm_prmt(v.x, v.z, 0x5410u);    // (x0, x4)
+                            o.y = sm_prmt(v.x, v.z, 0x7632u);    // (x1, x5)
+                            o.z = sm_prmt(v.y, v.w, 0x5410u);    // (x2, x6)
+                            o.w = sm_prmt(v.y, v.w, 0x7632u);    // (x3, x7)
+                            v = o;
+                        }
+                        sm_sts128(slot + xdst0 + (uint32_t)((mo >> 3) * G::kBlk * 1024 + (mo & 7) * 64), v);
+                        if ((lane & 7) == 0) sm_sts32(slot + xsum0 + (uint32_t)((mo >> 3) * G::kBlk * 32 + (mo & 7) * 4), sum);
+                    }
+                    fetch_next(buf[d]);                      // unit i + DEPTH
+                    __syncwarp();
+                    if (lane == 0) sm_bar_arrive(xfull_bar(xs));
+#ifdef QUANTA_SMALL_TRACE
+                    if (xw == 0 && lane == 0 && i < 2) SM_TRACE(25 + i);
+#endif
+                    if (++xs == p.XR) { xs = 0; ph ^= 1u; }
+                    ++i;
                 }
-                sm_sts128(slot + xdst[it], v);
-                if ((lane & 7) == 0) sm_sts32(slot + xsum_dst[it], sum);
             }
-            __syncwarp();
-            if (lane == 0) { sm_bar_arrive(xfull_bar(xs)); sm_bar_arrive(empty_bar(ws_)); }
-            if (++xs == kSmXRing) { xs = 0; ph ^= 1u; }
-            if (++ws_ == p.R) { ws_ = 0; wph_ ^= 1u; }
-        }
+        };
+        if (p.M <= kMStep) stage_all(std::integral_constant<int, 1>{}, std::integral_constant<int, 6>{});
+        else stage_all(std::integral_constant<int, kPer>{}, std::integral_constant<int, (NB == 1 ? 2 : 1)>{});
         return;
     }
 
     // ===== consumers =====
     const int gid = lane >> 2, tig = lane & 3;
-    const int rg = warp & 3, kq = warp >> 2;                 // rows 32 rg .. +32, block kq
+    const int rg = warp & 3, kq = warp >> 2;                 // rows 32 rg .. +32, blocks kBpw kq .. + kBpw of every stage
     // rows[sl][h]: slab sl (16 rows), MMA row gid + 8 h
     int rows[2][2];
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) { rows[sl][0] = (2 * rg + sl) * 16 + sm_row_of<BITS>(gid); rows[sl][1] = rows[sl][0] + 8; }
 
     const bool do_compute = !SM_DBG(p, 1), do_x = !SM_DBG(p, 2), do_epi = !SM_DBG(p, 4), do_wait = !SM_DBG(p, 8);
-    // Per-thread shared-memory offsets (the block b = kq is fixed per warp; rows + 8 / + 16 keep the swizzle
-    // phase, so every other address of a unit is one of these plus an immediate).
+    // Absolute shared-memory addresses of this thread's words in slot 0 (rows + 8 / + 16 keep the swizzle phase, so
+    // every other address of a stage is one of these plus an immediate).  Made opaque so that they live in registers:
+    // ptxas otherwise rematerialises the lane / warp arithmetic inside the stage loop.
     const int r00 = rows[0][0];
-    const uint32_t w_off = BITS == 4
-        ? (uint32_t)r00 * 128u + ((((uint32_t)(2 * kq + (tig >> 1))) ^ (uint32_t)(r00 & 7)) << 4) + (uint32_t)(tig & 1) * 8u
-        : (uint32_t)(kq >> 1) * 16384u + (uint32_t)r00 * 128u + ((((uint32_t)(4 * (kq & 1) + tig)) ^ (uint32_t)(r00 & 7)) << 4);
-    const uint32_t s_off = p.code_bytes + (uint32_t)r00 * 16u + (uint32_t)kq * 4u;
-    const uint32_t xb_off = p.x_off + (uint32_t)((kq * 2) * 512 + lane * 16);
-    const uint32_t xs_off = p.x_off + (uint32_t)(NB * 4096 + (kq * 8 + 2 * tig) * 4);
-    // Absolute shared-memory addresses of this thread's words in slot 0.  Made opaque so that they live in
-    // registers: ptxas otherwise rematerialises the whole lane / warp arithmetic above inside the unit loop
-    // (~30 of its ~160 instructions).
-    uint32_t w_base = smem + w_off, s_base = smem + s_off, xb_base = smem + xb_off, xs_base0 = smem + xs_off;
-    asm volatile("" : "+r"(w_base), "+r"(s_base), "+r"(xb_base), "+r"(xs_base0));
-    const uint32_t stage_bytes = p.stage_bytes, x_slot_bytes = p.x_slot_bytes;
+    uint32_t w_base[G::kBpw];
+#pragma unroll
+    for (int bb = 0; bb < G::kBpw; ++bb) {
+        const int b = kq * G::kBpw + bb;                     // block of the stage
+        const uint32_t off = BITS == 4
+            ? (uint32_t)(b >> 2) * 16384u + (uint32_t)r00 * 128u + ((((uint32_t)(2 * (b & 3) + (tig >> 1))) ^ (uint32_t)(r00 & 7)) << 4) + (uint32_t)(tig & 1) * 8u
+            : (uint32_t)(b >> 1) * 16384u + (uint32_t)r00 * 128u + ((((uint32_t)(4 * (b & 1) + tig)) ^ (uint32_t)(r00 & 7)) << 4);
+        w_base[bb] = smem + off;
+        asm volatile("" : "+r"(w_base[bb]));
+    }
+    constexpr uint32_t kRowPitch = (uint32_t)(G::kBlk * 4);  // bytes per row of a scale / zero-point tile
+    uint32_t s_base = smem + G::kCodeBytes + (uint32_t)r00 * kRowPitch + (uint32_t)(kq * G::kBpw) * 4u;
+    uint32_t xb_base = smem + p.x_off + (uint32_t)((kq * G::kBpw) * 1024 + lane * 16);
+    uint32_t xs_base0 = smem + p.x_off + (uint32_t)(NB * G::kBlk * 1024 + ((kq * G::kBpw) * 8 + 2 * tig) * 4);
+    asm volatile("" : "+r"(s_base), "+r"(xb_base), "+r"(xs_base0));
+    const uint32_t x_slot_bytes = p.x_slot_bytes;
+    const int ring = p.R, xring = p.XR;
 
     float tot[2][NB][4];
 #pragma unroll
@@ -552,108 +592,136 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (tid == 0) SM_TRACE(5);
     while (walk.next(tile, s0, s1, final_seg)) {
         for (int step = s0; step < s1; ++step) {
-            // The staging warps signal xfull only after they have seen the stage's `full` barrier complete (all of
-            // its TMA bytes are in shared memory by then), so one wait covers weights and activations.
+            if (do_wait) sm_bar_wait(full_bar(wslot), wph);
+#ifdef QUANTA_SMALL_TRACE
+            if (tid == 0 && tr_unit == 0) SM_TRACE(27);
+#endif
             if (do_x) sm_bar_wait(xfull_bar(xs_cur), xph);
-            else if (do_wait) sm_bar_wait(full_bar(wslot), wph);
+#ifdef QUANTA_SMALL_TRACE
+            if (tid == 0 && tr_unit == 0) SM_TRACE(28);
+#endif
 
             if (do_compute) {
-                const uint32_t w_cur = w_base + (uint32_t)wslot * stage_bytes, s_cur = s_base + (uint32_t)wslot * stage_bytes;
-                const uint32_t xb_cur = xb_base + (uint32_t)xs_cur * x_slot_bytes, xs_addr = xs_base0 + (uint32_t)xs_cur * x_slot_bytes;
-                // ---- every shared-memory read of the unit goes out first (they are ordered asm statements;
-                //      the arithmetic below is free for the compiler to interleave) ----
-                uint32_t wraw[2][2][BITS == 4 ? 2 : 4];      // [slab][row half][words]
+                const uint32_t st_off = (uint32_t)wslot * G::kStageBytes, x_off = (uint32_t)xs_cur * x_slot_bytes;
+                // scales / zero-points of the warp's blocks: rows (slab, half), kBpw adjacent blocks each
+                // (M <= 8: both blocks in one 8-byte read up front; M > 8: per block, late — registers)
+                constexpr bool kParamsUpFront = NB == 1;
+                float sc[2][2][G::kBpw], zc[2][2][G::kBpw];
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t wa = w_cur + (uint32_t)(sl * 2048 + h * 1024);
-                        if (BITS == 4) {
-                            const uint2 w = sm_lds64(wa);
-                            wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y;
+                        if (!kParamsUpFront) break;
+                        const uint32_t sa = s_base + st_off + (uint32_t)(sl * 16 + h * 8) * kRowPitch;
+                        if (G::kBpw == 2) {
+                            const uint2 a = sm_lds64(sa), z = sm_lds64(sa + G::kParamTile);
+                            sc[sl][h][0] = __uint_as_float(a.x); sc[sl][h][G::kBpw - 1] = __uint_as_float(a.y);
+                            zc[sl][h][0] = __uint_as_float(z.x); zc[sl][h][G::kBpw - 1] = __uint_as_float(z.y);
                         } else {
-                            const uint4 w = sm_lds128(wa);
-                            wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y; wraw[sl][h][BITS == 4 ? 0 : 2] = w.z; wraw[sl][h][BITS == 4 ? 1 : 3] = w.w;
+                            sc[sl][h][0] = sm_lds32(sa);
+                            zc[sl][h][0] = sm_lds32(sa + G::kParamTile);
                         }
                     }
-                uint4 xb[NB][2];
-                uint2 xs2[NB];
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    xb[nb][0] = sm_lds128(xb_cur + (uint32_t)(nb * 4096));
-                    xb[nb][1] = sm_lds128(xb_cur + (uint32_t)(nb * 4096 + 512));
-                    xs2[nb] = sm_lds64(xs_addr + (uint32_t)(nb * 128));
-                }
-                float sc[2][2], zc[2][2];
                 const float off = BITS == 4 ? T::kOffset : 0.0f;
 #pragma unroll
-                for (int sl = 0; sl < 2; ++sl)
+                for (int bb = 0; bb < G::kBpw; ++bb) {
+                    // ---- every shared-memory read of the block goes out first (ordered asm statements; the
+                    //      arithmetic below is free for the compiler to interleave) ----
+                    const uint32_t w_cur = w_base[bb] + st_off;
+                    uint32_t wraw[2][2][BITS == 4 ? 2 : 4];  // [slab][row half][words]
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        sc[sl][h] = sm_lds32(s_cur + (uint32_t)(sl * 256 + h * 128));
-                        zc[sl][h] = sm_lds32(s_cur + (uint32_t)(sl * 256 + h * 128 + 2048));
+                    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t wa = w_cur + (uint32_t)(sl * 2048 + h * 1024);
+                            if (BITS == 4) {
+                                const uint2 w = sm_lds64(wa);
+                                wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y;
+                            } else {
+                                const uint4 w = sm_lds128(wa);
+                                wraw[sl][h][0] = w.x; wraw[sl][h][1] = w.y; wraw[sl][h][BITS == 4 ? 0 : 2] = w.z; wraw[sl][h][BITS == 4 ? 1 : 3] = w.w;
+                            }
+                        }
+                    uint4 xb[NB];                            // the B fragments of two k steps; re-read for k = 2
+                    uint2 xs2[NB];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        xb[nb] = sm_lds128(xb_base + x_off + (uint32_t)((nb * G::kBlk + bb) * 1024));
+                        xs2[nb] = sm_lds64(xs_base0 + x_off + (uint32_t)((nb * G::kBlk + bb) * 32));
                     }
-                // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
-                //      are independent (2 slabs x NB accumulators) ----
-                float c[2][NB][4];
+                    // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
+                    //      are independent (2 slabs x NB accumulators) ----
+                    float c[2][NB][4];
 #pragma unroll
-                for (int sl = 0; sl < 2; ++sl)
+                    for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) { c[sl][nb][0] = c[sl][nb][1] = c[sl][nb][2] = c[sl][nb][3] = 0.0f; }
+                        for (int nb = 0; nb < NB; ++nb) { c[sl][nb][0] = c[sl][nb][1] = c[sl][nb][2] = c[sl][nb][3] = 0.0f; }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t a[2][4];                        // {row lo, row+8 lo, row hi, row+8 hi}
+                    for (int k = 0; k < 4; ++k) {
+                        if (k == 2) {
 #pragma unroll
-                    for (int sl = 0; sl < 2; ++sl) {
-                        if (BITS == 4) {
-                            // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k
-                            // the shifts by 4 and 12 are multiplications (IMAD.HI by 2^28 / 2^20 from the parameter bank,
-                            // opaque to ptxas): they issue on the FMA pipe while the LOP3s keep the ALU pipe busy
-                            const uint32_t r0 = wraw[sl][0][k >> 1], r1 = wraw[sl][1][k >> 1];
-                            const uint32_t w0 = (k & 1) ? (r0 >> 8) : r0, w1 = (k & 1) ? (r1 >> 8) : r1;
-                            const uint32_t m = (k & 1) ? p.mul12 : p.mul4;
-                            a[sl][0] = sm_and_or(w0, 0x000F000Fu, T::kMagic);
-                            a[sl][1] = sm_and_or(w1, 0x000F000Fu, T::kMagic);
-                            a[sl][2] = sm_and_or(__umulhi(r0, m), 0x000F000Fu, T::kMagic);
-                            a[sl][3] = sm_and_or(__umulhi(r1, m), 0x000F000Fu, T::kMagic);
-                        } else {
-                            uint32_t p0[2], p1[2];
-                            sm_pairs8<ACT>(wraw[sl][0][k], p0); sm_pairs8<ACT>(wraw[sl][1][k], p1);
-                            a[sl][0] = p0[0]; a[sl][1] = p1[0]; a[sl][2] = p0[1]; a[sl][3] = p1[1];
+                            for (int nb = 0; nb < NB; ++nb) xb[nb] = sm_lds128(xb_base + x_off + (uint32_t)((nb * G::kBlk + bb) * 1024 + 512));
+                        }
+                        uint32_t a[2][4];                    // {row lo, row+8 lo, row hi, row+8 hi}
+#pragma unroll
+                        for (int sl = 0; sl < 2; ++sl) {
+                            if (BITS == 4) {
+                                // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k.  (The shifts stay
+                                // on the ALU pipe: as IMAD.HI they measured 25 % slower, tools/micro/unit_mix.cu.)
+                                const uint32_t w0 = wraw[sl][0][k >> 1] >> (8 * (k & 1)), w1 = wraw[sl][1][k >> 1] >> (8 * (k & 1));
+                                a[sl][0] = sm_and_or(w0, 0x000F000Fu, T::kMagic);
+                                a[sl][1] = sm_and_or(w1, 0x000F000Fu, T::kMagic);
+                                a[sl][2] = sm_and_or(w0 >> 4, 0x000F000Fu, T::kMagic);
+                                a[sl][3] = sm_and_or(w1 >> 4, 0x000F000Fu, T::kMagic);
+                            } else {
+                                uint32_t p0[2], p1[2];
+                                sm_pairs8<ACT>(wraw[sl][0][k], p0); sm_pairs8<ACT>(wraw[sl][1][k], p1);
+                                a[sl][0] = p0[0]; a[sl][1] = p1[0]; a[sl][2] = p0[1]; a[sl][3] = p1[1];
+                            }
+                        }
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            const uint4 xv4 = xb[nb];
+                            const uint32_t b0 = (k & 1) ? xv4.z : xv4.x, b1 = (k & 1) ? xv4.w : xv4.y;
+#pragma unroll
+                            for (int sl = 0; sl < 2; ++sl) T::mma(c[sl][nb], a[sl], b0, b1);
                         }
                     }
 #pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) {
-                        const uint4 xv4 = xb[nb][k >> 1];
-                        const uint32_t b0 = (k & 1) ? xv4.z : xv4.x, b1 = (k & 1) ? xv4.w : xv4.y;
+                    for (int sl = 0; sl < 2; ++sl) {
+                        if (!kParamsUpFront) {
 #pragma unroll
-                        for (int sl = 0; sl < 2; ++sl) T::mma(c[sl][nb], a[sl], b0, b1);
-                    }
-                }
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t sa = s_base + st_off + (uint32_t)(sl * 16 + h * 8) * kRowPitch + (uint32_t)(bb * 4);
+                                sc[sl][h][bb] = sm_lds32(sa);
+                                zc[sl][h][bb] = sm_lds32(sa + G::kParamTile);
+                            }
+                        }
+                        const float s_0 = sc[sl][0][bb], s_1 = sc[sl][1][bb];
+                        const float z0 = __fmaf_rn(-off, s_0, zc[sl][0][bb]), z1 = __fmaf_rn(-off, s_1, zc[sl][1][bb]);
 #pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
-                    const float z0 = __fmaf_rn(-off, sc[sl][0], zc[sl][0]), z1 = __fmaf_rn(-off, sc[sl][1], zc[sl][1]);
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) {
-                        const float xs_a = __uint_as_float(xs2[nb].x), xs_b = __uint_as_float(xs2[nb].y);
-                        tot[sl][nb][0] = __fmaf_rn(sc[sl][0], c[sl][nb][0], __fmaf_rn(z0, xs_a, tot[sl][nb][0]));
-                        tot[sl][nb][1] = __fmaf_rn(sc[sl][0], c[sl][nb][1], __fmaf_rn(z0, xs_b, tot[sl][nb][1]));
-                        tot[sl][nb][2] = __fmaf_rn(sc[sl][1], c[sl][nb][2], __fmaf_rn(z1, xs_a, tot[sl][nb][2]));
-                        tot[sl][nb][3] = __fmaf_rn(sc[sl][1], c[sl][nb][3], __fmaf_rn(z1, xs_b, tot[sl][nb][3]));
+                        for (int nb = 0; nb < NB; ++nb) {
+                            const float xs_a = __uint_as_float(xs2[nb].x), xs_b = __uint_as_float(xs2[nb].y);
+                            tot[sl][nb][0] = __fmaf_rn(s_0, c[sl][nb][0], __fmaf_rn(z0, xs_a, tot[sl][nb][0]));
+                            tot[sl][nb][1] = __fmaf_rn(s_0, c[sl][nb][1], __fmaf_rn(z0, xs_b, tot[sl][nb][1]));
+                            tot[sl][nb][2] = __fmaf_rn(s_1, c[sl][nb][2], __fmaf_rn(z1, xs_a, tot[sl][nb][2]));
+                            tot[sl][nb][3] = __fmaf_rn(s_1, c[sl][nb][3], __fmaf_rn(z1, xs_b, tot[sl][nb][3]));
+                        }
                     }
                 }
             }
-            // every lane's reads of the stage have been consumed by the instructions above
+            // every lane's reads of the stage have been issued (and, in program order, consumed) above
             __syncwarp();
             if (lane == 0) { sm_bar_arrive(empty_bar(wslot)); if (do_x) sm_bar_arrive(xempty_bar(xs_cur)); }
-            if (++wslot == p.R) { wslot = 0; wph ^= 1u; }
-            if (++xs_cur == kSmXRing) { xs_cur = 0; xph ^= 1u; }
+            if (++wslot == ring) { wslot = 0; wph ^= 1u; }
+            if (++xs_cur == xring) { xs_cur = 0; xph ^= 1u; }
 #ifdef QUANTA_SMALL_TRACE
-            if (tid == 0 && tr_unit < 24) { SM_TRACE(8 + tr_unit); ++tr_unit; }
+            if (tid == 0 && tr_unit < 16) { SM_TRACE(8 + tr_unit); ++tr_unit; }
 #endif
         }
         if (tid == 0) SM_TRACE(6);
         if (do_epi) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");   // the first global accesses of the consumers follow
             // ===== end of this CTA's segment [s0, s1) of `tile`: the 4 K quarters meet in shared memory =====
             const bool whole = s0 == 0 && s1 == S;
             const uint32_t red = smem + p.red_off + (uint32_t)(rg * (2 * NB * 4) * 128 + lane * 4);
@@ -754,15 +822,17 @@ extern "C" __attribute__((visibility("default"))) int quanta_debug_small_trace(l
 
 // ---- host side --------------------------------------------------------------
 
-struct SmallTuning { int ring; int max_m; int ctas; int dbg; int pdl; };
+struct SmallTuning { int ring; int max_m; int ctas; int dbg; int pdl; int xring; int window; };
 static SmallTuning small_tuning() {
     static const SmallTuning t = []() {
-        SmallTuning v{0, 16, 0, 0, 1};
+        SmallTuning v{0, 16, 0, 0, 1, 0, kSmStartWindow};
         if (const char* e = getenv("QUANTA_B200_SMALL_RING")) { int s = atoi(e); if (s >= 2 && s <= kSmMaxRing) v.ring = s; }
         if (const char* e = getenv("QUANTA_B200_SMALL_MAX_M")) { int m = atoi(e); if (m >= 0 && m <= 16) v.max_m = m; }
         if (const char* e = getenv("QUANTA_B200_SMALL_CTAS")) { int c = atoi(e); if (c >= 1 && c <= kNumSMs) v.ctas = c; }
         if (const char* e = getenv("QUANTA_B200_SMALL_DBG")) v.dbg = atoi(e);
         if (const char* e = getenv("QUANTA_B200_SMALL_PDL")) v.pdl = atoi(e) != 0;
+        if (const char* e = getenv("QUANTA_B200_SMALL_XRING")) { int s = atoi(e); if (s >= 2 && s <= kSmMaxXRing) v.xring = s; }
+        if (const char* e = getenv("QUANTA_B200_SMALL_WINDOW")) { int s = atoi(e); if (s >= 1 && s <= kSmMaxRing) v.window = s; }
         return v;
     }();
     return t;
@@ -770,11 +840,13 @@ static SmallTuning small_tuning() {
 
 // The small-batch kernel serves M <= 16 with blockwise-64 parameters on K % 256 == 0.
 bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const void* scale, const void* zp) {
-    if (M > small_tuning().max_m || block != 64 || (K % kSmStepK) != 0) return false;
+    if (M > small_tuning().max_m || block != 64 || (K % kSmKGran) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) return false;
     const int64_t n_tiles = (N + kSmRows - 1) / kSmRows;
     if (n_tiles > kSmCounterBytes / 4) return false;
-    if ((unsigned long long)n_tiles * (unsigned long long)(K / kSmStepK) * (unsigned long long)(kNumSMs + 1) >= (1ull << 32)) return false;
+    const unsigned long long steps = (unsigned long long)(K / kSmKGran);       // >= S for both code widths
+    if ((unsigned long long)n_tiles * steps * (unsigned long long)(kNumSMs + 1) >= (1ull << 32)) return false;
+    if ((unsigned long long)n_tiles * steps * steps >= (1ull << 32)) return false;   // the division-free u / S (SmallParams::s_magic)
     return true;
 }
 
@@ -786,7 +858,9 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.m_pad = 8 * NB;
     p.n_tiles = (int)((N + kSmRows - 1) / kSmRows);
-    p.S = (int)(K / kSmStepK);
+    using G = SmGeom<BITS>;
+    if (reinterpret_cast<uintptr_t>(x) & 15) return QUANTA_EINVAL;          // 16-byte activation loads
+    p.S = (int)((K + G::kStepK - 1) / G::kStepK);
     p.U = (unsigned int)p.n_tiles * (unsigned int)p.S;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -804,26 +878,34 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     }
     if (small_tuning().ctas) sms = small_tuning().ctas < sms ? small_tuning().ctas : sms;
     p.G = (int)(p.U < (unsigned int)sms ? p.U : (unsigned int)sms);
-    p.code_bytes = BITS == 4 ? 16384u : 32768u;
-    p.stage_bytes = p.code_bytes + 4096u + (uint32_t)p.m_pad * 512u;       // codes | scales | zero-points | activations
-    p.x_slot_bytes = (uint32_t)(NB * 4096 + NB * 128);
-    const uint32_t x_bytes = (uint32_t)kSmXRing * p.x_slot_bytes;
+    p.q = p.U / (unsigned int)p.G;
+    p.r = p.U % (unsigned int)p.G;
+    // u / S as a multiplication: exact for u <= U because U * (magic * S - 2^32) < U * S < 2^32 (gemm_small_eligible)
+    p.s_magic = p.S == 1 ? 0u : (unsigned int)(((1ull << 32) + (unsigned long long)p.S - 1ull) / (unsigned long long)p.S);
+    p.x_slot_bytes = (uint32_t)(NB * G::kBlk * (1024 + 32));
     const uint32_t red_bytes = (uint32_t)(3 * 4 * 2 * NB * 4 * 128);
     const uint32_t bar_bytes = 256;
     const uint32_t budget = 226u * 1024u;
-    int ring = (int)((budget - x_bytes - red_bytes - bar_bytes) / p.stage_bytes);
+    // the weight ring gets what the activation ring leaves: prefer >= 4 stages, then the deepest activation ring
+    int ring = 0, xring = 0;
+    for (int xr = kSmMaxXRing; xr >= 2; --xr) {
+        if (small_tuning().xring && xr != small_tuning().xring) continue;
+        const int r = (int)((budget - (uint32_t)xr * p.x_slot_bytes - red_bytes - bar_bytes) / G::kStageBytes);
+        if (r > ring && (ring < 4)) { ring = r; xring = xr; }
+    }
     if (ring > kSmMaxRing) ring = kSmMaxRing;
     if (small_tuning().ring && small_tuning().ring < ring) ring = small_tuning().ring;
-    if (ring < 2) return QUANTA_EUNSUPPORTED;
+    if (ring < 2 || xring < 2) return QUANTA_EUNSUPPORTED;
     p.R = ring;
-    p.x_off = (uint32_t)ring * p.stage_bytes;
+    p.XR = xring;
+    p.window = small_tuning().window < ring ? small_tuning().window : ring;
+    const uint32_t x_bytes = (uint32_t)xring * p.x_slot_bytes;
+    p.x_off = (uint32_t)ring * G::kStageBytes;
     p.red_off = p.x_off + x_bytes;
     p.bar_off = p.red_off + red_bytes;
     const int smem = (int)(p.bar_off + bar_bytes);
     p.ldy = (int)ldy; p.col0 = (int)col0; p.n_out = n_out;
     p.dbg = small_tuning().dbg;
-    p.mul4 = 1u << 28;
-    p.mul12 = 1u << 20;
     bool aligned8 = true;
     for (int o = 0; o < kSmMaxOut; ++o) {
         p.y[o] = o < n_out ? ys[o] : nullptr;
@@ -843,17 +925,13 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
                                 kSmRows, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const uint64_t sstride = (uint64_t)(K / 64);
-    rc = make_tensor_map_2d(&tmap_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, scale, sstride, (uint64_t)N, sstride * 4, 4, kSmRows,
+    rc = make_tensor_map_2d(&tmap_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, scale, sstride, (uint64_t)N, sstride * 4, G::kBlk, kSmRows,
                             CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    rc = make_tensor_map_2d(&tmap_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zp, sstride, (uint64_t)N, sstride * 4, 4, kSmRows,
+    rc = make_tensor_map_2d(&tmap_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zp, sstride, (uint64_t)N, sstride * 4, G::kBlk, kSmRows,
                             CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
 
-    CUtensorMap tmap_x;
-    rc = make_tensor_map_2d(&tmap_x, SmTraits<ACT>::kOffset == 128.0f ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                            2, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kSmStepK, (uint32_t)p.m_pad, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
     auto kern = gemm_small_kernel<ACT, BITS, NB>;
     if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     cudaLaunchConfig_t cfg = {};
@@ -866,7 +944,7 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = small_tuning().pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_s, tmap_z, tmap_x, bias, counters, partial, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_w, tmap_s, tmap_z, x, bias, counters, partial, p);
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
 }
 

@@ -109,10 +109,11 @@ def test_gemm_larger_blocksizes(bits, blocksize):
 @pytest.mark.parametrize("bits", [4, 8])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(128, 256, 1), (200, 512, 7), (136, 1536, 9), (384, 2048, 16), (1000, 4096, 3),
-                                   (256, 6144, 12), (128, 8192, 8)])
+                                   (256, 6144, 12), (128, 8192, 8), (264, 768, 5), (300, 1280, 16), (512, 11008, 2)])
 def test_small_batch_kernel(bits, dtype, shape):
     """M <= 16, K % 256 == 0 takes the weight-stream kernel (csrc/gemm_small.cu): one and several K ranges per
-    row tile (partials + last-arriver reduction), ragged N, batch rows past M zero-filled."""
+    row tile (partials + last-arriver reduction), ragged N, batch rows past M zero-filled, and — 4-bit stages span
+    512 K values — K that ends in the middle of a stage (256, 768, 1280, 11008: the tail is zero-filled)."""
     from quanta_b200.nn import linear_wna16
     N, K, M = shape
     w, x, b, q, s, z = make_case(N, K, M, bits, dtype, seed=3 * N + K + M + bits)
@@ -125,6 +126,35 @@ def test_small_batch_kernel(bits, dtype, shape):
     assert err < 4e-3
     for _ in range(3):                     # deterministic, counters left clean
         assert torch.equal(linear_wna16(xd, q, s, z, bd, bits=bits, blocksize=64, out_features=N), y)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_gemm_right_behind_the_kernel_that_wrote_its_weights(bits):
+    """The GEMM kernels are launched with programmatic stream serialization and start streaming their WEIGHTS before
+    their dependency wait.  That is sound only because the kernels that write codes / scales never release their
+    dependents early (common.cuh, pdl_wait): quantize fresh weights and multiply right behind, no synchronisation
+    in between, many times; every result must equal the one computed after a device synchronise."""
+    import quanta_b200 as Q
+    from quanta_b200.nn import linear_wna16
+    N, K, M = 4096, 4096, 8
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    ws = [torch.randn(N, K, device="cuda") * 0.02 * (i + 1) for i in range(4)]
+    quant = (lambda w: Q.quantize_4bit(w, blocksize=64, packed=True)) if bits == 4 else (lambda w: Q.quantize_8bit(w, blocksize=64))
+    want = []
+    for w in ws:
+        q, s, z = quant(w)
+        torch.cuda.synchronize()
+        want.append(linear_wna16(x, q, s, z, None, bits=bits, blocksize=64, out_features=N).clone())
+    torch.cuda.synchronize()
+    bad = 0
+    for rep in range(30):
+        outs = []
+        for w in ws:                                       # quantize -> GEMM -> quantize -> GEMM ..., back to back
+            q, s, z = quant(w)
+            outs.append(linear_wna16(x, q, s, z, None, bits=bits, blocksize=64, out_features=N))
+        torch.cuda.synchronize()
+        bad += sum(0 if torch.equal(a, b) else 1 for a, b in zip(outs, want))
+    assert bad == 0
 
 
 def test_gemm_repeated_calls_leave_workspace_clean():

@@ -41,7 +41,7 @@ buf = np.zeros((148, 40), dtype=np.int64)
 st = lib.quanta_debug_small_trace(C.c_void_p(buf.ctypes.data))
 assert st == 0, st
 g0 = buf[:, 38].min()
-names = {32: "producer thread enters", 33: "weight barriers initialised", 34: "producer loop starts", 1: "producer first issue", 2: "producer dep-wait done", 3: "first stage landed", 4: "producer done", 5: "consumers enter",
+names = {32: "producer thread enters", 33: "weight barriers initialised", 34: "producer loop starts", 1: "producer first issue", 2: "producer dep-wait done", 3: "first stage landed", 4: "producer done", 5: "consumers enter", 24: "x warp 0 enters", 25: "x unit 0 staged", 26: "x unit 1 staged", 27: "cons: stage 0 full seen", 28: "cons: x 0 seen",
          6: "last segment loop end", 7: "walk end", 36: "reducer: contributors seen", 37: "kernel end (tid 0)"}
 np.set_printoptions(linewidth=200)
 print("globaltimer entry skew (ns): min 0, median %d, max %d;  exit - first entry: median %d, max %d" % (
@@ -49,7 +49,7 @@ print("globaltimer entry skew (ns): min 0, median %d, max %d;  exit - first entr
 for slot, nm in names.items():
     v = buf[:, slot]
     print("%-28s cycles: min %6d  median %6d  max %6d" % (nm, v.min(), np.median(v), v.max()))
-units = buf[:, 8:32]
+units = buf[:, 8:24]
 for c in (0, 1, 73, 146, 147):
     u = units[c][units[c] > 0]
     print("cta %3d: entry +%d ns, units end at" % (c, buf[c, 38] - g0), u.tolist(), " deltas", np.diff(u).tolist())
