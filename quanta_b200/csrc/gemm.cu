@@ -202,6 +202,10 @@ struct GemmParams {
     int S;                  // raw-code stages per tile: ceil(total_kb / 4)
     int G;                  // CTAs
     unsigned int U;         // work units: tiles * S  (U * G < 2^32, checked on the host)
+    unsigned int uq, ur;    // U / G, U % G: CTA c owns units [c uq + min(c, ur), + uq + (c < ur))
+    unsigned int s_magic;   // ceil(2^32 / S) (0: S == 1): u / S without a division — a 32-bit division is ~100
+    unsigned int nt_magic;  // ceil(2^32 / n_tiles) (0: n_tiles == 1)   instructions on every role's critical path
+    int my_acc;             // nacc / nmma
     int nbuf;               // accumulator buffers in TMEM (1 or 2)
     int nacc;               // independent accumulators per buffer (power of 2): consecutive MMAs rotate over them
     int nmma;               // MMA-issuing warps (2 when nacc >= 2: tcgen05.mma dispatch is per-warp bound)
@@ -220,16 +224,26 @@ struct GemmParams {
     int dbg;                // experiment switches (QUANTA_B200_GEMM_DBG): 1 = no MMA, 2 = no dequant math/store
 };
 
+// Division-free index arithmetic (exactness of the multiplications is checked on the host, gemm_launch).
+__device__ __forceinline__ unsigned int div_magic(unsigned int u, unsigned int magic) { return magic ? __umulhi(u, magic) : u; }
+__device__ __forceinline__ unsigned int first_unit(unsigned int c, const GemmParams& p) { return c * p.uq + (c < p.ur ? c : p.ur); }
+__device__ __forceinline__ int tile_of_unit(unsigned int u, const GemmParams& p) { return (int)div_magic(u, p.s_magic); }
+// tile -> (n tile, m tile): tiles are numbered n-fastest
+__device__ __forceinline__ void split_tile(int tile, const GemmParams& p, int& n_idx, int& m_idx) {
+    m_idx = (int)div_magic((unsigned int)tile, p.nt_magic);
+    n_idx = tile - m_idx * p.n_tiles;
+}
+
 // Contiguous range of work units of one CTA, walked tile by tile.
 struct SegWalk {
-    unsigned int u, u1, S;
+    unsigned int u, u1, S, magic;
     __device__ __forceinline__ void init(const GemmParams& p, unsigned int cta) {
-        u = p.U * cta / (unsigned int)p.G; u1 = p.U * (cta + 1u) / (unsigned int)p.G; S = (unsigned int)p.S;
+        u = first_unit(cta, p); u1 = first_unit(cta + 1u, p); S = (unsigned int)p.S; magic = p.s_magic;
     }
     // next segment: stages [s0, s1) of `tile`; false when the range is exhausted
     __device__ __forceinline__ bool next(int& tile, int& s0, int& s1) {
         if (u >= u1) return false;
-        const unsigned int t = u / S;
+        const unsigned int t = div_magic(u, magic);
         const unsigned int b = u - t * S, left = u1 - u;
         tile = (int)t; s0 = (int)b;
         s1 = (left < S - b) ? (int)(b + left) : (int)S;
@@ -240,11 +254,8 @@ struct SegWalk {
 
 // CTA whose unit range contains unit `u`
 __device__ __forceinline__ int cta_of_unit(unsigned int u, const GemmParams& p) {
-    const unsigned int G = (unsigned int)p.G;
-    unsigned int c = (unsigned int)(((unsigned long long)u * G) / p.U);
-    while (c + 1 < G && p.U * (c + 1) / G <= u) ++c;
-    while (c > 0 && p.U * c / G > u) --c;
-    return (int)c;
+    const unsigned int big = p.ur * (p.uq + 1u);
+    return (int)(u < big ? u / (p.uq + 1u) : p.ur + (u - big) / p.uq);      // reducers only, once per tile
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -342,7 +353,9 @@ template <typename ACT, int CG, int NOUT>
 __device__ __noinline__ void fixup_reduce(const GemmParams& p, const GemmOutputs<NOUT>& outs, const ACT* __restrict__ bias,
                                              const float* __restrict__ partial, int tile, int crank, int j, int nthreads) {
     using AT = ActTraits<ACT>;
-    const int n_tile = (tile % p.n_tiles) * CG + crank, m_tile = tile / p.n_tiles;
+    int n_idx, m_tile;
+    split_tile(tile, p, n_idx, m_tile);
+    const int n_tile = n_idx * CG + crank;
     const int m0 = m_tile * p.mb;
     const int m_valid = min(p.mb, p.M - m0);
     const int f4 = 4 * (j & 31), mq = j >> 5, mstep = nthreads >> 5;
@@ -359,7 +372,7 @@ __device__ __noinline__ void fixup_reduce(const GemmParams& p, const GemmOutputs
 #pragma unroll
         for (int i = 0; i < kFixRows; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c = c_first; c <= c_last; ++c) {
-            const int wc = (tile == (int)((p.U * (unsigned int)c / (unsigned int)p.G) / (unsigned int)p.S)) ? 0 : 1;
+            const int wc = (tile == tile_of_unit(first_unit((unsigned int)c, p), p)) ? 0 : 1;
             const float* src = partial + (((size_t)c * 2 + wc) * CG + crank) * slot_elems + f4;
             float4 v[kFixRows];
 #pragma unroll
@@ -469,7 +482,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         int slot = 0, issued = 0;
         uint32_t ph = 0;
         while (walk.next(tile, s0, s1)) {
-            const int n0 = ((tile % p.n_tiles) * CG + (int)crank) * kTileN;
+            int n_idx, m_idx;
+            split_tile(tile, p, n_idx, m_idx);
+            const int n0 = (n_idx * CG + (int)crank) * kTileN;
             for (int s = s0; s < s1; ++s) {
                 if (issued >= p.raw_stages) mbar_wait(&raw_empty[slot], ph ^ 1);
                 if (elect_one()) {
@@ -509,7 +524,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         int slot = 0, issued = 0;
         uint32_t ph = 0;
         while (walk.next(tile, s0, s1)) {
-            const int m0 = (tile / p.n_tiles) * p.mb + (int)crank * (p.mb / CG);     // this CTA's half of the rows
+            int n_idx, m_idx;
+            split_tile(tile, p, n_idx, m_idx);
+            const int m0 = m_idx * p.mb + (int)crank * (p.mb / CG);                  // this CTA's half of the rows
             for (int s = s0; s < s1; ++s) {
                 for (int j = 0; j < kKbPerStage; j += p.xkb) {
                     if (issued >= p.x_stages) mbar_wait(&x_empty[slot], ph ^ 1);
@@ -555,7 +572,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const uint32_t idesc = (1u << 4) | (AT::kFmt << 7) | (AT::kFmt << 10) |
                                ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)((kTileN * CG) >> 4) << 24);
         const uint32_t kb_desc = p.x_kb_bytes >> 4;          // descriptor step between 64-K blocks of one slot
-        const uint32_t my_acc = (uint32_t)(p.nacc / p.nmma);          // accumulators of this warp (power of 2)
+        const uint32_t my_acc = (uint32_t)p.my_acc;                   // accumulators of this warp (power of 2)
         int sx = 0, seg = 0, sc = 0;
         uint32_t px = 0;
         while (walk.next(tile, s0, s1)) {
@@ -618,7 +635,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
             const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);
-            const int n_tile = (tile % p.n_tiles) * CG + (int)crank, m_tile = tile / p.n_tiles;
+            int n_idx, m_tile;
+            split_tile(tile, p, n_idx, m_tile);
+            const int n_tile = n_idx * CG + (int)crank;
             const int gn = n_tile * kTileN + row, m0 = m_tile * p.mb;
             const bool n_ok = gn < p.N;
             const int m_valid = min(p.mb, p.M - m0);
@@ -626,8 +645,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const bool last_seg = walk.u >= walk.u1;                  // no further segment for this CTA
             const float b = (bias != nullptr && n_ok) ? AT::to_float(bias[gn]) : 0.0f;
             // this CTA's partial slot for the tile: 0 if the tile is the first one the CTA touches, else 1
-            const unsigned int u_first = p.U * cta / (unsigned int)p.G;
-            const int which = (tile == (int)(u_first / (unsigned int)p.S)) ? 0 : 1;
+            const int which = (tile == tile_of_unit(first_unit(cta, p), p)) ? 0 : 1;
             float* mine = partial + (((size_t)cta * 2 + which) * CG + crank) * (size_t)(kTileN * p.mb);
 
             TRACE2(4, etid == 0);
@@ -644,7 +662,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const bool vec_ok = p.vec_store && gn4 + 3 < p.N;
             // accumulators the MMA warps wrote in this segment: each warp issues 4 MMAs per 64-K block of
             // its half of the stage (all of it with one issuer), rotating over its own my_acc accumulators
-            const int my_acc = p.nacc / p.nmma;
+            const int my_acc = p.my_acc;
             const int last_nkb = (s1 == p.S) ? p.total_kb - (p.S - 1) * kKbPerStage : kKbPerStage;
             int kb_w[2];
             if (p.nmma == 1) { kb_w[0] = (s1 - s0 - 1) * kKbPerStage + last_nkb; kb_w[1] = 0; }
@@ -776,7 +794,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         bool a_ok = ahead.next(a_tile, a_s, a_s1);
         float sv[4], zv[4];
         auto fetch_params = [&](int t, int s) {
-            const int gn = ((t % p.n_tiles) * CG + (int)crank) * kTileN + row;
+            int n_idx, m_idx;
+            split_tile(t, p, n_idx, m_idx);
+            const int gn = (n_idx * CG + (int)crank) * kTileN + row;
             const int64_t rbase = (int64_t)(gn < p.N ? gn : p.N - 1) * p.scale_stride;
             const int kb = s * kKbPerStage;
 #pragma unroll
@@ -966,6 +986,20 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
     p.U = (unsigned int)tiles * (unsigned int)p.S;
     p.G = choose_units(tiles, p.S, mb, BITS == 4 ? 16384 : 32768, CG);
     { const int v = env_int("QUANTA_B200_GEMM_CTAS", 0); if (v >= 1 && v <= kNumSMs / CG && (unsigned int)v <= p.U) p.G = v; }
+    p.uq = p.U / (unsigned int)p.G;
+    p.ur = p.U % (unsigned int)p.G;
+    {
+        // x / d == __umulhi(x, ceil(2^32 / d)) for every x <= xmax when xmax * (magic * d - 2^32) < 2^32
+        auto magic_for = [](unsigned int d, unsigned long long xmax, unsigned int* out) {
+            if (d == 1) { *out = 0u; return true; }
+            const unsigned long long m = ((1ull << 32) + d - 1ull) / d;
+            *out = (unsigned int)m;
+            return xmax * (m * d - (1ull << 32)) < (1ull << 32);
+        };
+        if (!magic_for((unsigned int)p.S, p.U, &p.s_magic) || !magic_for((unsigned int)p.n_tiles, (unsigned long long)tiles, &p.nt_magic))
+            return QUANTA_EUNSUPPORTED;
+    }
+    p.my_acc = p.nacc / p.nmma;
     p.x_kb_bytes = (uint32_t)(mb / CG) * 128u;              // this CTA's rows of one 64-K block
     p.xkb = p.x_kb_bytes <= 8192u ? 4 : (p.x_kb_bytes <= 16384u ? 2 : 1);    // activation slots of at most 32 KB
     p.x_slot_bytes = p.x_kb_bytes * (uint32_t)p.xkb;
