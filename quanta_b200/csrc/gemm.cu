@@ -1092,7 +1092,7 @@ bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const v
 template <typename ACT, int BITS>
 int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
                       int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                      cudaStream_t st);
+                      cudaStream_t st, int nf4);
 
 template <typename ACT, int BITS>
 static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
@@ -1102,8 +1102,8 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     void* one[1] = {y};
     if (!ys) { ys = one; n_out = 1; ldy = N; col0 = 0; }
     // M <= 16: the weight-stream kernel (HBM-bound regime; gemm_small.cu)
-    if (!nf4 && gemm_small_eligible(M, N, K, block, scale, zp))
-        return gemm_small_launch<ACT, BITS>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+    if (gemm_small_eligible(M, N, K, block, scale, zp))
+        return gemm_small_launch<ACT, BITS>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, nf4);
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     const int n_tiles = (int)((N + kTileN - 1) / kTileN);

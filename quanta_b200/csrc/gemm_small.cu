@@ -63,14 +63,22 @@ constexpr int kSmCounterBytes = 64 * 1024; // same workspace header as gemm.cu (
 // One stage = 256 BYTES of codes per weight row (two SWIZZLE_128B boxes of [128 rows x 128 B]): HBM serves 256-byte
 // row pieces at its full rate, 128-byte ones (the 4-bit kernel's first form: 256 K per stage) at ~75 % of it
 // (measured: 4.8 vs 6.7 TB/s in the steady state of this kernel).
-template <int BITS> struct SmGeom {
+template <int BITS, bool NF4 = false> struct SmGeom {
     static constexpr int kStepK = 2048 / BITS;                       // K values per stage: 512 (4-bit) / 256 (8-bit)
     static constexpr int kBlk = kStepK / 64;                         // 64-K blocks per stage: 8 / 4
     static constexpr int kBpw = kBlk / 4;                            // blocks per consumer warp and stage: 2 / 1
     static constexpr uint32_t kCodeBytes = 32768u;
     static constexpr uint32_t kParamTile = (uint32_t)(kSmRows * kBlk * 4);   // one [128 rows x kBlk] fp32 tile
-    static constexpr uint32_t kStageBytes = kCodeBytes + 2u * kParamTile;    // codes | scales | zero-points
+    static constexpr uint32_t kStageBytes = kCodeBytes + (NF4 ? 1u : 2u) * kParamTile;   // codes | scales (NF4: abs_max) | zero-points
 };
+constexpr uint32_t kSmLutBytes = 256u * 128u;   // NF4: byte -> (level[lo nibble], level[hi nibble]) in the activation type, one copy per lane
+
+// NF4 levels (Quanta/functional/quantization.py:101-118; the same table as nf4.cu / gemm.cu)
+__constant__ float kSmNf4Levels[16] = {
+    -1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f, -0.28444138169288635f,
+    -0.18477343022823334f, -0.09105003625154495f, 0.0f, 0.07958029955625534f, 0.16093020141124725f,
+    0.24611230194568634f, 0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f,
+    0.7229568362236023f, 1.0f};
 
 // The experiment switches cost ~25 instructions per unit in the consumers' loop: compiled in only on request.
 #ifdef QUANTA_SMALL_DBG
@@ -106,6 +114,7 @@ struct SmallParams {
                             // 2 no x staging, 4 no epilogue, 8 no TMA
     uint32_t x_off;         // x ring
     uint32_t x_slot_bytes;  // NB * kBlk * (1024 fragment bytes + 32 block-sum bytes)
+    uint32_t lut_off;       // NF4 pair table (kSmLutBytes), unused otherwise
     uint32_t red_off;       // [3][4 row groups][2 slabs][NB][4][32] floats: the K quarters of a tile meet here
     uint32_t bar_off;       // mbarriers + flags
     void* y[kSmMaxOut];
@@ -328,13 +337,14 @@ __device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __rest
     }
 }
 
-template <typename ACT, int BITS, int NB>
+template <typename ACT, int BITS, int NB, bool NF4>
 __global__ void __launch_bounds__(kSmThreads, 1)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
                   const __grid_constant__ CUtensorMap tmap_z, const ACT* __restrict__ x, const ACT* __restrict__ bias,
                   unsigned int* __restrict__ counters, float* __restrict__ partial, const __grid_constant__ SmallParams p) {
     using T = SmTraits<ACT>;
-    using G = SmGeom<BITS>;
+    using G = SmGeom<BITS, NF4>;
+    static_assert(!NF4 || BITS == 4, "NF4 codes are 4-bit");
     extern __shared__ __align__(1024) uint8_t sm_raw[];
 
     const uint32_t smem = smem_u32(sm_raw);
@@ -416,7 +426,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     sm_tma_2d(dst, &tmap_w, bar, cb, n0, pol);
                     sm_tma_2d(dst + 16384u, &tmap_w, bar, cb + 128, n0, pol);
                     sm_tma_2d(dst + G::kCodeBytes, &tmap_s, bar, kb / 64, n0, pol);
-                    sm_tma_2d(dst + G::kCodeBytes + G::kParamTile, &tmap_z, bar, kb / 64, n0, pol);
+                    if (!NF4) sm_tma_2d(dst + G::kCodeBytes + G::kParamTile, &tmap_z, bar, kb / 64, n0, pol);
                     if (++slot == p.R) { slot = 0; ph ^= 1u; }
                 }
             }
@@ -520,7 +530,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                         sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-                        if (BITS == 4) {
+                        if (BITS == 4 && !NF4) {
                             uint4 o;
                             o.x = sm_prmt(v.x, v.z, 0x5410u);    // (x0, x4)
                             o.y = sm_prmt(v.x, v.z, 0x7632u);    // (x1, x5)
@@ -577,6 +587,20 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     asm volatile("" : "+r"(s_base), "+r"(xb_base), "+r"(xs_base0));
     const uint32_t x_slot_bytes = p.x_slot_bytes;
     const int ring = p.R, xring = p.XR;
+    // NF4: the 16 levels are not an affine function of the code, so the exact-integer trick does not apply; a code BYTE
+    // is looked up instead: table[b] = (level[b & 15], level[b >> 4]) as a 16-bit pair — the two K-adjacent weights of
+    // the byte, in natural K order — replicated once per lane (entry b of lane l at b * 128 + 4 l: every lane of a
+    // lookup hits its own bank).  2 ALU instructions + 1 LDS per byte instead of 7 ALU per word.
+    uint32_t lut_lane = smem + p.lut_off + (uint32_t)lane * 4u;
+    if (NF4) {
+        for (int e = tid; e < 256 * 32; e += kSmConsThreads) {
+            const int b = e >> 5;
+            const uint32_t pr = T::pack(kSmNf4Levels[b & 15], kSmNf4Levels[b >> 4]);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem + p.lut_off + (uint32_t)e * 4u), "r"(pr) : "memory");
+        }
+        sm_cons_sync();
+        asm volatile("" : "+r"(lut_lane));
+    }
 
     float tot[2][NB][4];
 #pragma unroll
@@ -614,12 +638,15 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         if (!kParamsUpFront) break;
                         const uint32_t sa = s_base + st_off + (uint32_t)(sl * 16 + h * 8) * kRowPitch;
                         if (G::kBpw == 2) {
-                            const uint2 a = sm_lds64(sa), z = sm_lds64(sa + G::kParamTile);
+                            const uint2 a = sm_lds64(sa);
                             sc[sl][h][0] = __uint_as_float(a.x); sc[sl][h][G::kBpw - 1] = __uint_as_float(a.y);
-                            zc[sl][h][0] = __uint_as_float(z.x); zc[sl][h][G::kBpw - 1] = __uint_as_float(z.y);
+                            if (!NF4) {
+                                const uint2 z = sm_lds64(sa + G::kParamTile);
+                                zc[sl][h][0] = __uint_as_float(z.x); zc[sl][h][G::kBpw - 1] = __uint_as_float(z.y);
+                            }
                         } else {
                             sc[sl][h][0] = sm_lds32(sa);
-                            zc[sl][h][0] = sm_lds32(sa + G::kParamTile);
+                            if (!NF4) zc[sl][h][0] = sm_lds32(sa + G::kParamTile);
                         }
                     }
                 const float off = BITS == 4 ? T::kOffset : 0.0f;
@@ -647,7 +674,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {
                         xb[nb] = sm_lds128(xb_base + x_off + (uint32_t)((nb * G::kBlk + bb) * 1024));
-                        xs2[nb] = sm_lds64(xs_base0 + x_off + (uint32_t)((nb * G::kBlk + bb) * 32));
+                        if (!NF4) xs2[nb] = sm_lds64(xs_base0 + x_off + (uint32_t)((nb * G::kBlk + bb) * 32));
                     }
                     // ---- 4 MMAs (K = 16 each) per slab and batch block: k outermost, so that consecutive MMAs
                     //      are independent (2 slabs x NB accumulators) ----
@@ -665,7 +692,18 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         uint32_t a[2][4];                    // {row lo, row+8 lo, row hi, row+8 hi}
 #pragma unroll
                         for (int sl = 0; sl < 2; ++sl) {
-                            if (BITS == 4) {
+                            if (NF4) {
+                                // word k / 2, bytes 2 (k & 1) and 2 (k & 1) + 1: K-adjacent pairs in natural order
+                                const uint32_t r0 = wraw[sl][0][k >> 1], r1 = wraw[sl][1][k >> 1];
+                                const uint32_t i00 = (k & 1) ? ((r0 >> 9) & 0x7F80u) : ((r0 << 7) & 0x7F80u);
+                                const uint32_t i01 = (k & 1) ? ((r0 >> 17) & 0x7F80u) : ((r0 >> 1) & 0x7F80u);
+                                const uint32_t i10 = (k & 1) ? ((r1 >> 9) & 0x7F80u) : ((r1 << 7) & 0x7F80u);
+                                const uint32_t i11 = (k & 1) ? ((r1 >> 17) & 0x7F80u) : ((r1 >> 1) & 0x7F80u);
+                                a[sl][0] = __float_as_uint(sm_lds32(lut_lane + i00));
+                                a[sl][1] = __float_as_uint(sm_lds32(lut_lane + i10));
+                                a[sl][2] = __float_as_uint(sm_lds32(lut_lane + i01));
+                                a[sl][3] = __float_as_uint(sm_lds32(lut_lane + i11));
+                            } else if (BITS == 4) {
                                 // word k / 2: pairs (n0,n4) (n1,n5) for even k, (n2,n6) (n3,n7) for odd k.  (The shifts stay
                                 // on the ALU pipe: as IMAD.HI they measured 25 % slower, tools/micro/unit_mix.cu.)
                                 const uint32_t w0 = wraw[sl][0][k >> 1] >> (8 * (k & 1)), w1 = wraw[sl][1][k >> 1] >> (8 * (k & 1));
@@ -694,8 +732,19 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             for (int h = 0; h < 2; ++h) {
                                 const uint32_t sa = s_base + st_off + (uint32_t)(sl * 16 + h * 8) * kRowPitch + (uint32_t)(bb * 4);
                                 sc[sl][h][bb] = sm_lds32(sa);
-                                zc[sl][h][bb] = sm_lds32(sa + G::kParamTile);
+                                if (!NF4) zc[sl][h][bb] = sm_lds32(sa + G::kParamTile);
                             }
+                        }
+                        if (NF4) {
+                            // y += abs_max * raw: the table holds the levels themselves, no offset term
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                tot[sl][nb][0] = __fmaf_rn(sc[sl][0][bb], c[sl][nb][0], tot[sl][nb][0]);
+                                tot[sl][nb][1] = __fmaf_rn(sc[sl][0][bb], c[sl][nb][1], tot[sl][nb][1]);
+                                tot[sl][nb][2] = __fmaf_rn(sc[sl][1][bb], c[sl][nb][2], tot[sl][nb][2]);
+                                tot[sl][nb][3] = __fmaf_rn(sc[sl][1][bb], c[sl][nb][3], tot[sl][nb][3]);
+                            }
+                            continue;
                         }
                         const float s_0 = sc[sl][0][bb], s_1 = sc[sl][1][bb];
                         const float z0 = __fmaf_rn(-off, s_0, zc[sl][0][bb]), z1 = __fmaf_rn(-off, s_1, zc[sl][1][bb]);
@@ -850,7 +899,7 @@ bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const v
     return true;
 }
 
-template <typename ACT, int BITS, int NB>
+template <typename ACT, int BITS, int NB, bool NF4>
 static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias,
                                 void* const* ys, int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K,
                                 void* workspace, size_t ws_bytes, cudaStream_t st) {
@@ -858,7 +907,7 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.m_pad = 8 * NB;
     p.n_tiles = (int)((N + kSmRows - 1) / kSmRows);
-    using G = SmGeom<BITS>;
+    using G = SmGeom<BITS, NF4>;
     if (reinterpret_cast<uintptr_t>(x) & 15) return QUANTA_EINVAL;          // 16-byte activation loads
     p.S = (int)((K + G::kStepK - 1) / G::kStepK);
     p.U = (unsigned int)p.n_tiles * (unsigned int)p.S;
@@ -890,7 +939,8 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     // 3 stages 17.0 us, 2 + 4: 19.3, 4 + 3: 18.4; its staging warps prefetch only one unit in registers there) — and
     // the weight ring gets what is left.
     const int xring = small_tuning().xring ? small_tuning().xring : (NB == 1 ? kSmMaxXRing : 3);
-    int ring = (int)((budget - (uint32_t)xring * p.x_slot_bytes - red_bytes - bar_bytes) / G::kStageBytes);
+    const uint32_t lut_bytes = NF4 ? kSmLutBytes : 0u;
+    int ring = (int)((budget - (uint32_t)xring * p.x_slot_bytes - red_bytes - bar_bytes - lut_bytes) / G::kStageBytes);
     if (ring > kSmMaxRing) ring = kSmMaxRing;
     if (small_tuning().ring && small_tuning().ring < ring) ring = small_tuning().ring;
     if (ring < 2 || xring < 2) return QUANTA_EUNSUPPORTED;
@@ -899,7 +949,8 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     p.window = small_tuning().window < ring ? small_tuning().window : ring;
     const uint32_t x_bytes = (uint32_t)xring * p.x_slot_bytes;
     p.x_off = (uint32_t)ring * G::kStageBytes;
-    p.red_off = p.x_off + x_bytes;
+    p.lut_off = p.x_off + x_bytes;
+    p.red_off = p.lut_off + lut_bytes;
     p.bar_off = p.red_off + red_bytes;
     const int smem = (int)(p.bar_off + bar_bytes);
     p.ldy = (int)ldy; p.col0 = (int)col0; p.n_out = n_out;
@@ -930,7 +981,7 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
                             CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
 
-    auto kern = gemm_small_kernel<ACT, BITS, NB>;
+    auto kern = gemm_small_kernel<ACT, BITS, NB, NF4>;
     if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.G);
@@ -949,14 +1000,20 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
 template <typename ACT, int BITS>
 int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
                       int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                      cudaStream_t st) {
-    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
-    return gemm_small_launch_nb<ACT, BITS, 2>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+                      cudaStream_t st, int nf4) {
+    if (nf4) {
+        // 4-bit codes index the NF4 table, `scale` holds abs_max per block, `zp` is not read
+        if (BITS != 4) return QUANTA_EINVAL;
+        if (M <= 8) return gemm_small_launch_nb<ACT, 4, 1, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+        return gemm_small_launch_nb<ACT, 4, 2, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+    }
+    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+    return gemm_small_launch_nb<ACT, BITS, 2, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
 }
 
-#define QUANTA_SMALL_INST(ACT, BITS)                                                                                          \
+#define QUANTA_SMALL_INST(ACT, BITS)                                                                                    \
     template int gemm_small_launch<ACT, BITS>(const ACT*, const uint8_t*, const float*, const float*, const ACT*, void* const*, \
-                                              int, int64_t, int64_t, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t);
+                                              int, int64_t, int64_t, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t, int);
 QUANTA_SMALL_INST(__nv_bfloat16, 4)
 QUANTA_SMALL_INST(__nv_bfloat16, 8)
 QUANTA_SMALL_INST(__half, 4)

@@ -213,6 +213,32 @@ def test_nf4_gemm_matches_composition_oracle(dtype, shape):
     assert rel_err(y.float().cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(128, 256, 1), (1000, 4096, 3), (136, 1536, 9), (264, 768, 5), (512, 11008, 2),
+                                   (384, 2048, 16), (2048, 8192, 8)])
+def test_nf4_small_batch_kernel(dtype, shape):
+    """M <= 16, K % 256 == 0: NF4 goes through the weight-stream kernel as well (byte -> level-pair table in shared
+    memory, csrc/gemm_small.cu).  Same oracle as above; the levels enter the MMA rounded to the activation type and the
+    block's abs_max is applied in fp32, so the result is at least as close as the tcgen05 path's."""
+    import quanta_b200 as Q
+    from quanta_b200.nn import linear_nf4a16
+    N, K, M = shape
+    g = torch.Generator().manual_seed(7 * N + K + M)
+    w = torch.randn(N, K, generator=g) * 0.02
+    x = torch.randn(M, K, generator=g).to(dtype)
+    b = (torch.randn(N, generator=g) * 0.1).to(dtype)
+    q, levels, am = Q.quantize_4bit(w.cuda(), quant_type="nf4", blocksize=64, packed=True)
+    xd, bd = x.cuda(), b.cuda()
+    y = linear_nf4a16(xd, q, am, bd, blocksize=64, out_features=N)
+    idx = O.unpack4(q.cpu().numpy())[: N * K].reshape(N, K)
+    wd = O.dequantize_nf4(idx, am.cpu().numpy(), 64)
+    ref = x.float().numpy().astype(np.float64) @ wd.astype(np.float64).T + b.float().numpy().astype(np.float64)
+    err = rel_err(y.float().cpu().numpy(), ref)
+    assert err < TOL, f"rel err {err:.3e} for {shape} {dtype}"
+    for _ in range(3):                     # deterministic, counters left clean
+        assert torch.equal(linear_nf4a16(xd, q, am, bd, blocksize=64, out_features=N), y)
+
+
 def test_linear4bit_default_is_nf4():
     from quanta_b200.nn import Linear4bit
     torch.manual_seed(1)
