@@ -295,11 +295,11 @@ def secondary_single_gpu(device, pk, torch, Q):
             del ws
             torch.cuda.empty_cache()
 
-    def stream_case(name, shape, alg_bytes, make, fn, copies):
+    def stream_case(name, shape, alg_bytes, make, fn, copies, reps=20):
         nonlocal launches
         ins = [make(i) for i in range(copies)]
-        us = graph_time_us(lambda i: fn(ins[i % copies]), 20, torch)
-        launches += 20
+        us = graph_time_us(lambda i: fn(ins[i % copies]), reps, torch)
+        launches += reps
         gbs = alg_bytes / us / 1e3
         out["streams"].append({"op": name, "shape": list(shape), "alg_bytes": alg_bytes, "us": round(us, 2),
                                "GBps": round(gbs, 1), "frac": round(gbs / HBM, 3)})
@@ -331,6 +331,17 @@ def secondary_single_gpu(device, pk, torch, Q):
             g = torch.Generator(device=device).manual_seed(i)
             return torch.randint(0, 16, (n,), device=device, dtype=torch.uint8, generator=g)
         stream_case("pack_4bit_tensor (P1)", shape, n * 1.5, codes, lambda c: Q.pack_4bit_tensor(c), max(copies, 12))
+
+    # the blockwise dequantize as ONE launch over a decoder layer's 7 matrices (quanta_dequantize_block_batch)
+    layer = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+    elems = sum(a * b for (a, b) in layer)
+
+    def layer_codes(i):
+        ws = [randn(sh, 10 * i + j) for j, sh in enumerate(layer)]
+        qs = Q.quantize_4bit_many(ws, blocksize=BLOCK, packed=True)
+        return [t[0] for t in qs], [t[1] for t in qs], [t[2] for t in qs]
+    stream_case("dequantize_4bit_many packed block-64 -> fp32: one decoder layer, 7 matrices, 1 launch", (elems,), elems * 4.625,
+                layer_codes, lambda t: Q.dequantize_4bit_many(t[0], t[1], t[2], blocksize=BLOCK, packed=True, shapes=layer), 3, reps=6)
     return out, launches
 
 

@@ -122,6 +122,17 @@ QUANTA_API int quanta_dequantize_affine(const uint8_t* q, int packed4, int64_t r
                              int mode, int64_t block, const float* scale, const float* zp,
                              void* out, int out_dtype, void* stream);
 
+/* The same blockwise dequantization (mode BLOCK) over `count` tensors in
+ * ceil(count / 16) launches — the fused form of calling
+ * QuantizationState.dequantize_tensor (Quanta/functional/state.py:246-281),
+ * i.e. dequantize_*bit, once per recorded tensor.  qs / scales / zps / outs are HOST arrays
+ * of device pointers, numels[i] the CODE count of tensor i (a positive multiple
+ * of `block`, block % 4 == 0); results are identical to `count` calls of
+ * quanta_dequantize_affine(..., QUANTA_MODE_BLOCK, ...).                      */
+QUANTA_API int quanta_dequantize_block_batch(const uint8_t* const* qs, const int64_t* numels, int count, int packed4,
+                                  int64_t block, const float* const* scales, const float* const* zps,
+                                  void* const* outs, int out_dtype, void* stream);
+
 /* ---- NF4 codebook: Quanta/functional/quantization.py:101-118, :59-61 --------
  * quantize_4bit(tensor, quant_type="nf4"): abs_max = max|x|, normalized =
  * x / abs_max, code = argmin_l |normalized - level_l| (first index on ties,

@@ -11,5 +11,6 @@ __version__ = "0.1.0"
 
 from . import functional  # noqa: F401
 from .functional import (quantize_8bit, quantize_4bit, dequantize_8bit, dequantize_4bit,  # noqa: F401
-                         quantize_4bit_many, quantize_8bit_many, quantize_nf4_many)
+                         quantize_4bit_many, quantize_8bit_many, quantize_nf4_many,
+                         dequantize_4bit_many, dequantize_8bit_many)
 from .utils import pack_4bit_tensor, unpack_4bit_tensor  # noqa: F401

@@ -27,6 +27,7 @@ SIGNATURES = {
     "quanta_quantize_affine": (_int, [_vp, _int, _i64, _i64, _int, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quanta_quantize_block_batch": (_int, [_vp, _vp, _int, _int, _i64, _int, _int, _vp, _vp, _vp, _vp]),
     "quanta_dequantize_affine": (_int, [_vp, _int, _i64, _i64, _int, _i64, _vp, _vp, _vp, _int, _vp]),
+    "quanta_dequantize_block_batch": (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp, _vp, _int, _vp]),
     "quanta_nf4_levels": (_int, [_vp]),
     "quanta_quantize_nf4": (_int, [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp]),
     "quanta_dequantize_nf4": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _int, _vp]),

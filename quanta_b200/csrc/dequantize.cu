@@ -228,6 +228,84 @@ static int dequant_launch(const uint8_t* q, int64_t rows, int64_t cols, int mode
     return cuda_status(cudaGetLastError());
 }
 
+// ---- many tensors, one launch (blockwise, convention A) ---------------------------------------------------
+// Dequantizing every recorded tensor of a model — the reference calls QuantizationState.dequantize_tensor
+// (Quanta/functional/state.py:246-281) once per tensor — as one grid: every matrix
+// launched on its own pays ~4 us of ramp and drain on a 10-40 us stream.  The tensors' 4-code groups are cut into
+// chunks of kDqChunk groups; the chunk index space is the concatenation of the tensors' chunks, a persistent grid
+// walks it.  Descriptors ride in the kernel parameters.
+constexpr int kDqMultiMax = 16;
+constexpr int kDqChunk = 256 * 4;                  // groups of 4 codes per chunk: 4 steps of a 256-thread CTA
+struct DqMultiArgs {
+    const uint8_t* q[kDqMultiMax];
+    const float* scale[kDqMultiMax];
+    const float* zp[kDqMultiMax];
+    void* out[kDqMultiMax];
+    int64_t n4[kDqMultiMax];                       // groups of 4 codes
+    int64_t chunk_base[kDqMultiMax + 1];           // first global chunk of tensor i; [count] = total
+    int count;
+};
+
+template <typename OUT, bool PACKED>
+__global__ void __launch_bounds__(256) dequant_flat_multi_kernel(const __grid_constant__ DqMultiArgs a, int block_shift,
+                                                                 int64_t block) {
+    pdl_enter();
+    const int64_t total = a.chunk_base[a.count];
+    int ti = 0;
+    for (int64_t c = blockIdx.x; c < total; c += gridDim.x) {
+        while (ti + 1 < a.count && c >= a.chunk_base[ti + 1]) ++ti;
+        const uint8_t* __restrict__ q = a.q[ti];
+        const float* __restrict__ scale = a.scale[ti];
+        const float* __restrict__ zp = a.zp[ti];
+        OUT* __restrict__ out = static_cast<OUT*>(a.out[ti]);
+        const int64_t n4 = a.n4[ti];
+        const int64_t g0 = (c - a.chunk_base[ti]) * kDqChunk + threadIdx.x;
+        uint32_t w[4]; float ps[4], pz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t g = g0 + k * 256;
+            w[k] = 0u; ps[k] = pz[k] = 0.0f;
+            if (g < n4) {
+                const int64_t i = g * 4;
+                const int64_t b = block_shift >= 0 ? (i >> block_shift) : (i / block);
+                w[k] = load_codes4<PACKED>(q, i);
+                ps[k] = __ldg(scale + b); pz[k] = __ldg(zp + b);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t g = g0 + k * 256;
+            if (g < n4) {
+                const DqParam p{ps[k], pz[k], 0.0f};
+                store4<OUT>(out + g * 4, dq_value<kDqA>(byte_to_f32<0>(w[k]), p, false, 0.f), dq_value<kDqA>(byte_to_f32<1>(w[k]), p, false, 0.f),
+                            dq_value<kDqA>(byte_to_f32<2>(w[k]), p, false, 0.f), dq_value<kDqA>(byte_to_f32<3>(w[k]), p, false, 0.f));
+            }
+        }
+    }
+}
+
+template <typename OUT, bool PACKED>
+static int dequant_multi_launch(const uint8_t* const* qs, const int64_t* numels, int count, int64_t block, const float* const* scales,
+                                const float* const* zps, void* const* outs, cudaStream_t st) {
+    for (int first = 0; first < count; first += kDqMultiMax) {
+        DqMultiArgs a;
+        a.count = count - first < kDqMultiMax ? count - first : kDqMultiMax;
+        a.chunk_base[0] = 0;
+        for (int i = 0; i < a.count; ++i) {
+            a.q[i] = qs[first + i]; a.scale[i] = scales[first + i]; a.zp[i] = zps[first + i]; a.out[i] = outs[first + i];
+            a.n4[i] = numels[first + i] / 4;
+            a.chunk_base[i + 1] = a.chunk_base[i] + (a.n4[i] + kDqChunk - 1) / kDqChunk;
+        }
+        for (int i = a.count; i < kDqMultiMax; ++i) { a.q[i] = nullptr; a.scale[i] = nullptr; a.zp[i] = nullptr; a.out[i] = nullptr; a.n4[i] = 0; a.chunk_base[i + 1] = a.chunk_base[a.count]; }
+        const int64_t total = a.chunk_base[a.count];
+        const int64_t cap = (int64_t)kNumSMs * 8;
+        cudaError_t e = launch_pdl(dequant_flat_multi_kernel<OUT, PACKED>, dim3((unsigned)(total < cap ? total : cap)), dim3(256), 0, st,
+                                   a, shift_of(block), block);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return cuda_status(cudaGetLastError());
+}
+
 template <bool PACKED, int CONV>
 static int dequant_dtype(const uint8_t* q, int64_t rows, int64_t cols, int mode, int64_t block, const float* scale,
                          const float* zp, void* out, int out_dtype, const int* flag, float off, cudaStream_t st) {
@@ -269,4 +347,34 @@ extern "C" int quanta_backend_dequantize(const uint8_t* q, int64_t rows, int64_t
     zp_allclose_zero_kernel<<<1, 256, 0, st>>>(zp, nchan, flag);
     const int mode = nchan == 1 ? QUANTA_MODE_TENSOR : QUANTA_MODE_DIM0;
     return dequant_dtype<false, kDqB>(q, rows, cols, mode, 0, scale, zp, out, QUANTA_F32, flag, bits == 8 ? 128.f : 8.f, st);
+}
+
+// The per-parameter dequantize loop of a model in ceil(count / 16) launches: tensor i = numels[i] codes (packed4: two
+// per byte), blockwise parameters scales[i] / zps[i] of numels[i] / block floats, output outs[i] (out_dtype).  Host
+// arrays of device pointers.  Every numel must be a positive multiple of `block`, block % 4 == 0; code pointers
+// 4-byte (2-byte when packed), outputs 16-byte (fp32) / 8-byte (16-bit) aligned.
+extern "C" int quanta_dequantize_block_batch(const uint8_t* const* qs, const int64_t* numels, int count, int packed4,
+                                             int64_t block, const float* const* scales, const float* const* zps,
+                                             void* const* outs, int out_dtype, void* stream) {
+    if (!qs || !numels || !scales || !zps || !outs || count < 0) return QUANTA_EINVAL;
+    if (block <= 0 || block % 4 != 0) return QUANTA_EINVAL;
+    if (out_dtype != QUANTA_F32 && out_dtype != QUANTA_F16 && out_dtype != QUANTA_BF16) return QUANTA_EINVAL;
+    const size_t out_align = out_dtype == QUANTA_F32 ? 16 : 8;
+    for (int i = 0; i < count; ++i) {
+        if (!qs[i] || !scales[i] || !zps[i] || !outs[i] || numels[i] <= 0 || numels[i] % block != 0) return QUANTA_EINVAL;
+        if (reinterpret_cast<uintptr_t>(qs[i]) % (packed4 ? 2 : 4) != 0 || reinterpret_cast<uintptr_t>(outs[i]) % out_align != 0) return QUANTA_EINVAL;
+    }
+    if (count == 0) return QUANTA_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (out_dtype) {
+        case QUANTA_F32:
+            return packed4 ? dequant_multi_launch<float, true>(qs, numels, count, block, scales, zps, outs, st)
+                           : dequant_multi_launch<float, false>(qs, numels, count, block, scales, zps, outs, st);
+        case QUANTA_F16:
+            return packed4 ? dequant_multi_launch<__half, true>(qs, numels, count, block, scales, zps, outs, st)
+                           : dequant_multi_launch<__half, false>(qs, numels, count, block, scales, zps, outs, st);
+        default:
+            return packed4 ? dequant_multi_launch<__nv_bfloat16, true>(qs, numels, count, block, scales, zps, outs, st)
+                           : dequant_multi_launch<__nv_bfloat16, false>(qs, numels, count, block, scales, zps, outs, st);
+    }
 }

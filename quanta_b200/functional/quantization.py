@@ -365,6 +365,68 @@ def _dequantize_linear(q_tensor, scale, zero_point, blocksize, packed, shape, ou
     return out
 
 
+def _dequantize_many(qs, scales, zero_points, blocksize, packed, shapes, out_dtype):
+    import ctypes as C
+    qs, scales, zero_points = list(qs), list(scales), list(zero_points)
+    if not (len(qs) == len(scales) == len(zero_points)):
+        raise ValueError("qs, scales and zero_points must have the same length")
+    if not qs:
+        return []
+    B = int(blocksize)
+    if B <= 0 or B % 4:
+        raise ValueError("blocksize must be a positive multiple of 4")
+    if out_dtype not in _host._DTYPE:
+        raise ValueError(f"unsupported out_dtype {out_dtype}")
+    shapes = list(shapes) if shapes is not None else [None] * len(qs)
+    dev = qs[0].device
+    cq, cs, cz, ns, out_shapes = [], [], [], [], []
+    for q, s, z, shape in zip(qs, scales, zero_points, shapes):
+        _host.require_cuda(q, "q_tensor")
+        if q.device != dev:
+            raise ValueError("all tensors of a batch must share one device")
+        q = q.detach()
+        if q.dtype != torch.uint8:
+            q = q.to(torch.uint8)
+        if not q.is_contiguous():
+            q = q.contiguous()
+        if packed:
+            out_shape = torch.Size(shape) if shape is not None else torch.Size([q.numel() * 2])
+        else:
+            out_shape = q.shape
+        n = out_shape.numel()
+        if packed and q.numel() != (n + 1) // 2:
+            raise ValueError(f"packed codes hold {q.numel()} bytes, shape {tuple(out_shape)} needs {(n + 1) // 2}")
+        if n == 0 or n % B:
+            raise ValueError(f"numel ({n}) must be a positive multiple of blocksize ({blocksize})")
+        s = torch.as_tensor(s, dtype=torch.float32, device=dev).contiguous()
+        z = torch.as_tensor(z, dtype=torch.float32, device=dev).contiguous()
+        if s.numel() != n // B or z.numel() != n // B:
+            raise ValueError("scale/zero_point do not match blocksize")
+        cq.append(q); cs.append(s); cz.append(z); ns.append(n); out_shapes.append(out_shape)
+    with _host.device_guard(dev):
+        outs = [torch.empty(sh, dtype=out_dtype, device=dev) for sh in out_shapes]
+        k = len(cq)
+        arr = C.c_void_p * k
+        st = _lib.lib().quanta_dequantize_block_batch(
+            arr(*[q.data_ptr() for q in cq]), (C.c_int64 * k)(*ns), k, int(bool(packed)), B,
+            arr(*[s.data_ptr() for s in cs]), arr(*[z.data_ptr() for z in cz]), arr(*[o.data_ptr() for o in outs]),
+            _host._DTYPE[out_dtype], _host.stream_ptr(dev))
+    _lib.check(st, "quanta_dequantize_block_batch")
+    return outs
+
+
+def dequantize_4bit_many(qs, scales, zero_points, blocksize=64, packed=True, shapes=None, out_dtype=torch.float32):
+    """Blockwise 4-bit dequantization of many tensors in as few launches as possible — the fused form of the
+    per-tensor calls of ``QuantizationState.dequantize_tensor`` (Quanta/functional/state.py:246-281).  Returns
+    ``[dequantize_4bit(q, s, z, blocksize=blocksize, packed=packed, shape=shape) for ...]`` (same bits)."""
+    return _dequantize_many(qs, scales, zero_points, blocksize, packed, shapes, out_dtype)
+
+
+def dequantize_8bit_many(qs, scales, zero_points, blocksize=64, out_dtype=torch.float32):
+    """Blockwise 8-bit twin of :func:`dequantize_4bit_many`."""
+    return _dequantize_many(qs, scales, zero_points, blocksize, False, None, out_dtype)
+
+
 def dequantize_8bit(q_tensor, scale_or_levels, zero_point_or_bias, quant_type="linear", blocksize=None,
                     out_dtype=torch.float32):
     """Dequantize an 8-bit tensor back to floating point:

@@ -351,6 +351,38 @@ def test_full_size_properties(Q):
     assert (q3 != q).float().mean().item() < 1e-3
 
 
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_batched_blockwise_dequantize_equals_per_tensor_calls(out_dtype):
+    """quanta_dequantize_block_batch: many tensors per launch, bit-identical to one dequantize call per tensor (and, in
+    fp32, to the oracle); > 16 tensors exercises several launches, sizes below one chunk and ragged last chunks."""
+    import quanta_b200 as Q
+    g = torch.Generator().manual_seed(22)
+    shapes = [(256, 512), (64, 64), (1000, 64), (4096, 1024), (32, 8192), (3, 64)] * 3 + [(11008, 512)]
+    ts = [(torch.randn(*s, generator=g) * 0.02).cuda() for s in shapes]
+    for bits, packed in ((4, True), (4, False), (8, False)):
+        quant = Q.quantize_4bit_many(ts, blocksize=64, packed=packed) if bits == 4 else Q.quantize_8bit_many(ts, blocksize=64)
+        qs, ss, zs = [t[0] for t in quant], [t[1] for t in quant], [t[2] for t in quant]
+        if bits == 4:
+            many = Q.dequantize_4bit_many(qs, ss, zs, blocksize=64, packed=packed, shapes=[t.shape for t in ts] if packed else None,
+                                          out_dtype=out_dtype)
+        else:
+            many = Q.dequantize_8bit_many(qs, ss, zs, blocksize=64, out_dtype=out_dtype)
+        assert len(many) == len(ts)
+        for t, q, sc, z, d in zip(ts, qs, ss, zs, many):
+            one = (Q.dequantize_4bit(q, sc, z, blocksize=64, packed=packed, shape=t.shape if packed else None, out_dtype=out_dtype)
+                   if bits == 4 else Q.dequantize_8bit(q, sc, z, blocksize=64, out_dtype=out_dtype))
+            assert d.shape == t.shape and d.dtype == out_dtype
+            assert torch.equal(d.view(torch.int16 if out_dtype != torch.float32 else torch.int32),
+                               one.view(torch.int16 if out_dtype != torch.float32 else torch.int32))
+    if out_dtype == torch.float32:
+        q, sc, z = Q.quantize_8bit(ts[3], blocksize=64)
+        d = Q.dequantize_8bit_many([q], [sc], [z], blocksize=64)[0]
+        ref = O.dequantize_affine(q.cpu().numpy().reshape(-1, 64), sc.cpu().numpy().reshape(-1, 1), z.cpu().numpy().reshape(-1, 1))
+        assert np.array_equal(d.cpu().numpy().reshape(-1, 64).view(np.uint32), np.asarray(ref, dtype=np.float32).view(np.uint32))
+    with pytest.raises(ValueError):
+        Q.dequantize_8bit_many([qs[0]], [ss[0]], [zs[0], zs[1]], blocksize=64)
+
+
 def test_batched_blockwise_quantize_equals_per_tensor_calls():
     """quanta_quantize_block_batch: many tensors per launch, bit-identical to one call per tensor
     (and therefore to the oracle); > 16 tensors exercises several launches, odd sizes the fallback."""
