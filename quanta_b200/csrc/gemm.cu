@@ -269,76 +269,36 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------
-// In a cluster the shared-window address of a CTA carries its rank in bit 24; clearing it names
-// the same offset in the even (leader) CTA of the pair.
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// ---- CTA-pair helpers (CG = 2) ------------------------------------------------------------
+// Two CTAs of a cluster work on ADJACENT 128-feature tiles over the same K range and the same batch rows.  Everything
+// is private to a CTA (weight ring, dequant groups, TMEM, MMA issue, epilogue) except the activation tile, which both
+// need: each CTA loads HALF of its rows and multicasts them into both CTAs' rings, so the pair pulls every activation
+// byte out of L2 once instead of twice (at 256 batch rows the activation traffic — 128 KB per 16 KB of codes — is what
+// bounds the kernel).  A slot may be refilled when BOTH CTAs' MMAs have read it: the commit that frees it is multicast
+// too.  (The first form of the pair, one cta_group::2 MMA for both CTAs, coupled the two dequant pipelines through one
+// barrier and measured 10-25 % slower than single CTAs; it is gone.)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// arrive on the leader CTA's copy of `bar` (a local arrive when this CTA is the leader)
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-// wait with cluster-scope acquire: the barrier is completed by the peer CTA's arrivals / TMA
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONEC_%=;\n\t"
-        "bra WAITC_%=;\n\t"
-        "DONEC_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-template <int CG> __device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity) {
-    if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
-}
-template <int CG> __device__ __forceinline__ void tmem_alloc_cg(uint32_t smem_dst, uint32_t ncols) {
+// completes `bar` in this CTA, or at the same offset in both CTAs of the pair
+template <int CG> __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     if (CG == 2) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-        tmem_alloc(smem_dst, ncols);
-    }
-}
-template <int CG> __device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
-    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-    else tmem_dealloc(taddr, ncols);
-}
-template <int CG>
-__device__ __forceinline__ void umma_f16_ts_cg(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    if (CG == 2) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-            "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-    } else {
-        umma_f16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
-    }
-}
-// completes `bar` in this CTA (CG = 1) or at the same offset in both CTAs of the pair (CG = 2)
-template <int CG> __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
-    if (CG == 2) {
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                      ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
     } else {
         umma_commit(bar);
     }
 }
-// activation tile load; in a pair both CTAs signal the leader's barrier
+// activation tile load; in a pair the rows land in both CTAs and signal both CTAs' barriers (same offsets)
 template <int CG>
 __device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, uint64_t policy) {
     if (CG == 2) {
         asm volatile(
-            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-            " [%0], [%1, {%3, %4}], [%2], %5;"
-            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+            " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"((uint16_t)3), "r"(c0), "r"(c1), "l"(policy)
             : "memory");
     } else {
         tma_load_2d_plain(dst, map, bar, c0, c1, policy);
@@ -437,11 +397,9 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
-    // CG = 2: the two CTAs of a cluster form a pair (tcgen05 cta_group::2): they walk the same unit
-    // range on adjacent 128-feature tiles, each loads half of the activation rows, and the leader
-    // (rank 0) issues one 256-feature MMA for both.  `cta` is the scheduling unit (CTA or pair).
+    // CG = 2: the two CTAs of a cluster form a pair: they walk the same unit range on adjacent 128-feature tiles
+    // and share the activation loads (see the pair helpers above).  `cta` is the scheduling unit (CTA or pair).
     const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
-    const bool leader = crank == 0;
     const unsigned int cta = blockIdx.x / CG;
 
     // shared memory: [raw ring: raw_stages x 16|32 KB][x ring: x_stages x (xkb x mb x 128 B)]
@@ -512,7 +470,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     } else if (warp == 1) {
         // ===== activation tiles: xkb 64-K blocks per slot =====
         if (lane == 0) {
-            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+            for (int s = 0; s < p.x_stages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], CG); }   // freed by both CTAs' MMAs
             fence_barrier_init();
             prefetch_tensormap(&tmap_x);
         }
@@ -526,15 +484,16 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         while (walk.next(tile, s0, s1)) {
             int n_idx, m_idx;
             split_tile(tile, p, n_idx, m_idx);
-            const int m0 = m_idx * p.mb + (int)crank * (p.mb / CG);                  // this CTA's half of the rows
+            const int m0 = m_idx * p.mb + (int)crank * (p.mb / CG);                  // this CTA loads (and multicasts) its half of the rows
+            const uint32_t half_off = crank * (uint32_t)(p.mb / CG) * 128u;          // where they go inside a 64-K block of the slot
             for (int s = s0; s < s1; ++s) {
                 for (int j = 0; j < kKbPerStage; j += p.xkb) {
                     if (issued >= p.x_stages) mbar_wait(&x_empty[slot], ph ^ 1);
                     if (elect_one()) {
-                        if (leader) mbar_arrive_expect_tx(&x_full[slot], p.x_slot_bytes * CG);    // both halves
+                        mbar_arrive_expect_tx(&x_full[slot], p.x_slot_bytes);               // all rows: own loads + the peer's
                         // blocks past the end of K are out of bounds and arrive zero-filled
                         for (int jj = 0; jj < p.xkb; ++jj)
-                            tma_load_x<CG>(x_addr(slot) + (uint32_t)jj * p.x_kb_bytes, &tmap_x, smem_u32(&x_full[slot]),
+                            tma_load_x<CG>(x_addr(slot) + (uint32_t)jj * p.x_kb_bytes + half_off, &tmap_x, smem_u32(&x_full[slot]),
                                            (s * kKbPerStage + j + jj) * kBlockK, m0, pol_x);
                     }
                     __syncwarp();
@@ -546,11 +505,10 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     } else {
         if (warp == 2) {
-            tmem_alloc_cg<CG>(smem_u32(&tmem_base_slot), kTmemCols);
+            tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
         } else if (warp == 3 && lane == 0) {
-            // a_full / d_empty live in the leader and collect both CTAs' arrivals
-            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], CG * kDqGroupWarps); mbar_init(&a_empty[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], p.nmma); mbar_init(&d_empty[s], CG * kEpiWarps); }
+            for (int s = 0; s < kDqGroups; ++s) { mbar_init(&a_full[s], kDqGroupWarps); mbar_init(&a_empty[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], p.nmma); mbar_init(&d_empty[s], kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -561,7 +519,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (leader && (warp == 2 || (warp == 3 && p.nmma == 2))) {
+    if (warp == 2 || (warp == 3 && p.nmma == 2)) {
         // ===== MMA issuers: the whole warp walks the schedule, one elected lane issues =====
         // A tcgen05.mma costs ~70 cycles of dispatch whatever its size (the tensor pipe itself needs only
         // N/2 cycles), so a stage is >= 1120 cycles of issue plus ~600 cycles of barrier waits and
@@ -570,7 +528,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // warp rotates over its own half of the accumulators (the epilogue adds all of them up).
         const int mw = warp - 2;
         const uint32_t idesc = (1u << 4) | (AT::kFmt << 7) | (AT::kFmt << 10) |
-                               ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)((kTileN * CG) >> 4) << 24);
+                               ((uint32_t)(p.mb >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
         const uint32_t kb_desc = p.x_kb_bytes >> 4;          // descriptor step between 64-K blocks of one slot
         const uint32_t my_acc = (uint32_t)p.my_acc;                   // accumulators of this warp (power of 2)
         int sx = 0, seg = 0, sc = 0;
@@ -578,13 +536,13 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         while (walk.next(tile, s0, s1)) {
             const int buf = p.nbuf == 2 ? (seg & 1) : 0;
             const uint32_t use = (uint32_t)(p.nbuf == 2 ? (seg >> 1) : seg);      // how often `buf` was used before
-            mbar_wait_x<CG>(&d_empty[buf], (use & 1) ^ 1);   // the epilogues have drained this accumulator
+            mbar_wait(&d_empty[buf], (use & 1) ^ 1);   // the epilogues have drained this accumulator
             const uint32_t tmem_d = tmem + kDBase + (uint32_t)((buf * p.nacc + mw * (int)my_acc) * p.mb);
             uint32_t touched = 0;                            // own accumulators already written in this segment
             for (int s = s0; s < s1; ++s, ++sc) {
                 const int nkb = min(kKbPerStage, p.total_kb - s * kKbPerStage);
                 const int g = sc & 1;                        // dequant group = A buffer
-                if (p.nmma == 1 || g == mw) mbar_wait_x<CG>(&a_full[g], (uint32_t)(sc >> 1) & 1u);   // the stage's 4 A tiles are in TMEM
+                if (p.nmma == 1 || g == mw) mbar_wait(&a_full[g], (uint32_t)(sc >> 1) & 1u);   // the stage's 4 A tiles are in TMEM
                 const uint32_t ta = tmem + (uint32_t)(g * kKbPerStage * kACols);
                 TRACE2(2, lane == 0);
 #pragma unroll
@@ -592,7 +550,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     const int jj = j & (p.xkb - 1);
                     const bool mine = p.nmma == 1 || (sc & 1) == mw;
                     if (mine) {
-                        if (jj == 0) mbar_wait_x<CG>(&x_full[sx], px);       // activation slot landed
+                        if (jj == 0) mbar_wait(&x_full[sx], px);       // activation slot landed
                         tc_fence_after();
                         const bool live = j < nkb && !(p.dbg & 1);
                         uint32_t acc_idx[4], acc_flag[4];    // computed by every lane: stays warp-uniform
@@ -607,12 +565,12 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                                 const uint64_t db = smem_desc_sw128(x_addr(sx)) + (uint64_t)(jj * kb_desc);
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)    // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
-                                    umma_f16_ts_cg<CG>(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
+                                    umma_f16_ts(tmem_d + acc_idx[k] * (uint32_t)p.mb, ta + (uint32_t)(j * kACols + 8 * k),
                                                 db + 2 * k, idesc, acc_flag[k]);
                             }
                             // both arrive when the MMAs above have read their operands
-                            if (jj == p.xkb - 1) umma_commit_cg<CG>(&x_empty[sx]);
-                            if (j == kKbPerStage - 1) umma_commit_cg<CG>(&a_empty[g]);
+                            if (jj == p.xkb - 1) umma_commit_pair<CG>(&x_empty[sx]);   // in a pair: frees the slot in both CTAs
+                            if (j == kKbPerStage - 1) umma_commit(&a_empty[g]);
                         }
                         __syncwarp();
                     }
@@ -620,7 +578,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 TRACE2(2, lane == 0);
             }
-            if (elect_one()) umma_commit_cg<CG>(&d_full[buf]);
+            if (elect_one()) umma_commit(&d_full[buf]);
             __syncwarp();
             ++seg;
         }
@@ -745,7 +703,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             TRACE2(4, etid == 0);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_leader(&d_empty[buf]); else mbar_arrive(&d_empty[buf]); }   // accumulator may be overwritten
+            if (lane == 0) mbar_arrive(&d_empty[buf]);   // accumulator may be overwritten
             if (!whole) {
                 // stream-K fix-up: the CTA that arrives last at the tile's counter reduces every partial
                 const unsigned int tu0 = (unsigned int)tile * (unsigned int)p.S;
@@ -897,7 +855,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (CG == 2) mbar_arrive_leader(&a_full[group]); else mbar_arrive(&a_full[group]);
+                        mbar_arrive(&a_full[group]);
                         mbar_arrive(&raw_empty[rslot]);
                     }
 
@@ -920,7 +878,7 @@ gemm_wna16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (CG == 2) { cluster_arrive(); cluster_wait(); }       // the peer may still be signalling into this CTA
-    if (warp == 2) { tc_fence_after(); tmem_dealloc_cg<CG>(tmem, kTmemCols); }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
 #ifdef QUANTA_GEMM_TRACE
     if (tr && tid == 0) {
         printf("end %lld\n", clock64() - t_start);
@@ -1000,7 +958,7 @@ static int gemm_launch_cg(GemmParams& p, const ACT* x, const uint8_t* wq, const 
             return QUANTA_EUNSUPPORTED;
     }
     p.my_acc = p.nacc / p.nmma;
-    p.x_kb_bytes = (uint32_t)(mb / CG) * 128u;              // this CTA's rows of one 64-K block
+    p.x_kb_bytes = (uint32_t)mb * 128u;                     // one 64-K block of the activation tile (all rows: a pair multicasts)
     p.xkb = p.x_kb_bytes <= 8192u ? 4 : (p.x_kb_bytes <= 16384u ? 2 : 1);    // activation slots of at most 32 KB
     p.x_slot_bytes = p.x_kb_bytes * (uint32_t)p.xkb;
     p.raw_bytes = (BITS == 4 ? 16384u : 32768u) + (p.vec4 ? 4096u : 0u);    // codes (+ scale / zero-point tiles)
@@ -1107,11 +1065,13 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     const int n_tiles = (int)((N + kTileN - 1) / kTileN);
-    // CTA pairs (tcgen05 cta_group::2: one 256-feature MMA per pair, each CTA loads half of the activation
-    // rows) are written into the kernel (template parameter CG) but measured 10-25 % slower than single CTAs in
-    // round 1 (later pipeline start, the two dequant pipelines are coupled through one A-full barrier), so only
-    // CG = 1 is instantiated.
-    const int cg = 1;
+    // CTA pairs (CG = 2: adjacent feature tiles, the activation tile loaded once and multicast to both CTAs) halve the
+    // L2 reads of the activations — and measured no faster (M = 256: 42.8 vs 42.1 us on 4096 x 14336, 32.1 vs 31.8 on
+    // 14336 x 4096; M = 64 / 128 1-4 % slower): every SM still has to take in the whole 128 KB tile per 256-K stage
+    // (41 B/cycle at the measured stage time), so the bound is the SM's inbound path, not L2.  Off unless
+    // QUANTA_B200_GEMM_PAIR=1 (kept working by tests/test_gpu_gemm.py::test_cta_pair_multicast_mode).
+    int cg = 1;
+    if (env_int("QUANTA_B200_GEMM_PAIR", 0) == 1 && n_tiles >= 2 && n_out == 1) cg = 2;
     const int mb_step = 16 * cg;                             // each CTA of a pair holds mb / 2 rows, a multiple of 16
     int mb = (int)((M + mb_step - 1) / mb_step * mb_step);
     if (mb > 256) mb = 256;
@@ -1138,6 +1098,7 @@ static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, cons
     p.vec4 = (bs == 0 && (p.scale_stride & 3) == 0 &&
               ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(zp)) & 15) == 0) ? 1 : 0;
     if (n_out > 1) return gemm_launch_cg<ACT, BITS, 1, kMaxOut>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
+    if (cg == 2) return gemm_launch_cg<ACT, BITS, 2, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
     return gemm_launch_cg<ACT, BITS, 1, 1>(p, x, wq, scale, zp, bias, ys, M, N, K, workspace, ws_bytes, st);
 }
 
