@@ -259,6 +259,25 @@ QUANTA_API int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uin
                               int64_t M, int64_t N, int64_t K,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* quanta_gemm_wna16_scatter with the ranks' synchronisation INSIDE the kernel
+ * (decode-sized batches: the separate barrier kernel costs as much as the GEMM).
+ * peer_flags: host array of `world` device pointers, peer_flags[r] = rank r's
+ * flag array of `world` unsigned ints in peer-mapped (symmetric) memory,
+ * zero-initialised once; epoch: a counter the caller increments on every call
+ * of the layer.  The last CTA of this rank's grid stores `epoch` into
+ * peer_flags[r][rank] of every peer after all of the grid's output stores are
+ * performed system-wide, and leaves only when peer_flags[rank][r] has reached
+ * `epoch` for every r: completion of the kernel on a rank means that every
+ * rank's columns are in that rank's y.  Returns QUANTA_EUNSUPPORTED when the
+ * shape is outside the small-batch kernel (M > 16, block != 64, K % 256 != 0);
+ * the caller then falls back to quanta_gemm_wna16_scatter + its own barrier. */
+QUANTA_API int quanta_gemm_wna16_scatter_sync(const void* x, int act_dtype, const uint8_t* wq, int bits,
+                              const float* scale, const float* zp, int64_t block,
+                              const void* bias, void* const* ys, int n_out, int64_t ldy, int64_t col0,
+                              int64_t M, int64_t N, int64_t K,
+                              void* workspace, size_t workspace_bytes,
+                              void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream);
+
 /* The same for NF4 weights — Linear4bit's default quant_type="nf4"
  * (nn/linear.py:58): wq nibble-packed NF4 codes [N, K/2], absmax float32
  * [N, K/block] (quanta_quantize_nf4 with block | K, block % 64 == 0);

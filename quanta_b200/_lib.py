@@ -15,6 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libquanta_b200.so")
 
 MODE_TENSOR, MODE_DIM0, MODE_BLOCK = 0, 1, 2
+E_INVAL, E_UNSUPPORTED, E_WORKSPACE, E_DRIVER = -1, -2, -3, -4        # include/quanta_b200.h
 F32, F16, BF16 = 0, 1, 2
 OP_QUANTIZE_AFFINE, OP_BACKEND_QUANTIZE, OP_BACKEND_DEQUANTIZE, OP_GEMM, OP_INT8_OUTLIER, OP_BASE_QUANTIZE = range(6)
 
@@ -48,6 +49,8 @@ SIGNATURES = {
     "quanta_gemm_wna16": (_int, [_vp, _int, _vp, _int, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "quanta_gemm_wna16_scatter": (_int, [_vp, _int, _vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _vp,
                                          _sz, _vp]),
+    "quanta_gemm_wna16_scatter_sync": (_int, [_vp, _int, _vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _vp,
+                                              _sz, _vp, _int, _int, C.c_uint, _vp]),
     "quanta_gemm_nf4a16": (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "quanta_int8_outlier_matmul": (_int, [_vp, _int, _vp, _vp, _f, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
 }

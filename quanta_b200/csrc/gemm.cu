@@ -1050,18 +1050,19 @@ bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const v
 template <typename ACT, int BITS>
 int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
                       int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                      cudaStream_t st, int nf4);
+                      cudaStream_t st, int nf4, const PeerSync* sync);
 
 template <typename ACT, int BITS>
 static int gemm_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, int64_t block,
                        const ACT* bias, ACT* y, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
                        cudaStream_t st, int nf4 = 0, void* const* ys = nullptr, int n_out = 1, int64_t ldy = 0,
-                       int64_t col0 = 0) {
+                       int64_t col0 = 0, const PeerSync* sync = nullptr) {
     void* one[1] = {y};
     if (!ys) { ys = one; n_out = 1; ldy = N; col0 = 0; }
     // M <= 16: the weight-stream kernel (HBM-bound regime; gemm_small.cu)
     if (gemm_small_eligible(M, N, K, block, scale, zp))
-        return gemm_small_launch<ACT, BITS>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, nf4);
+        return gemm_small_launch<ACT, BITS>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, nf4, sync);
+    if (sync) return QUANTA_EUNSUPPORTED;                    // the in-kernel completion exists in the small-batch kernel only
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     const int n_tiles = (int)((N + kTileN - 1) / kTileN);
@@ -1148,10 +1149,10 @@ extern "C" int quanta_gemm_nf4a16(const void* x, int act_dtype, const uint8_t* w
     return QUANTA_EINVAL;
 }
 
-extern "C" int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uint8_t* wq, int bits, const float* scale,
+static int gemm_scatter_entry(const void* x, int act_dtype, const uint8_t* wq, int bits, const float* scale,
                                          const float* zp, int64_t block, const void* bias, void* const* ys, int n_out,
                                          int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
+                                         size_t workspace_bytes, void* stream, const PeerSync* sync) {
     if (!x || !wq || !scale || !zp || !ys || n_out < 1 || n_out > kMaxOut || M <= 0 || N <= 0 || K <= 0) return QUANTA_EINVAL;
     if (ldy < col0 + N || col0 < 0) return QUANTA_EINVAL;
     for (int o = 0; o < n_out; ++o) if (!ys[o]) return QUANTA_EINVAL;
@@ -1162,13 +1163,38 @@ extern "C" int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uin
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == QUANTA_BF16) {
         using T = __nv_bfloat16;
-        return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0)
-                         : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0);
+        return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0, sync)
+                         : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0, sync);
     }
     if (act_dtype == QUANTA_F16) {
         using T = __half;
-        return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0)
-                         : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0);
+        return bits == 4 ? gemm_launch<T, 4>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0, sync)
+                         : gemm_launch<T, 8>((const T*)x, wq, scale, zp, block, (const T*)bias, nullptr, M, N, K, workspace, workspace_bytes, st, 0, ys, n_out, ldy, col0, sync);
     }
     return QUANTA_EINVAL;
+}
+
+extern "C" int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uint8_t* wq, int bits, const float* scale,
+                                         const float* zp, int64_t block, const void* bias, void* const* ys, int n_out,
+                                         int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    return gemm_scatter_entry(x, act_dtype, wq, bits, scale, zp, block, bias, ys, n_out, ldy, col0, M, N, K, workspace, workspace_bytes,
+                              stream, nullptr);
+}
+
+// The same, with the ranks' synchronisation inside the kernel: when it has completed on this rank, every rank's columns
+// have landed in this rank's buffer (see PeerSync in common.cuh) and no barrier kernel is needed behind it.
+// QUANTA_EUNSUPPORTED when the shape is not served by the small-batch kernel (M > 16, block != 64, K % 256 != 0):
+// the caller then uses quanta_gemm_wna16_scatter plus its own barrier.
+extern "C" int quanta_gemm_wna16_scatter_sync(const void* x, int act_dtype, const uint8_t* wq, int bits, const float* scale,
+                                              const float* zp, int64_t block, const void* bias, void* const* ys, int n_out,
+                                              int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace,
+                                              size_t workspace_bytes, void* const* peer_flags, int rank, int world,
+                                              unsigned int epoch, void* stream) {
+    if (!peer_flags || world < 2 || world > 8 || rank < 0 || rank >= world) return QUANTA_EINVAL;
+    PeerSync sync;
+    for (int r = 0; r < 8; ++r) sync.flags[r] = r < world ? peer_flags[r] : nullptr;
+    sync.rank = rank; sync.world = world; sync.epoch = epoch;
+    return gemm_scatter_entry(x, act_dtype, wq, bits, scale, zp, block, bias, ys, n_out, ldy, col0, M, N, K, workspace, workspace_bytes,
+                              stream, &sync);
 }

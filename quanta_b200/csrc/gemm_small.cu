@@ -118,7 +118,12 @@ struct SmallParams {
     uint32_t red_off;       // [3][4 row groups][2 slabs][NB][4][32] floats: the K quarters of a tile meet here
     uint32_t bar_off;       // mbarriers + flags
     void* y[kSmMaxOut];
+    // tensor-parallel completion inside the kernel (PeerSync, common.cuh); sync_world == 0: off
+    unsigned int* sync_flags[kSmMaxOut];
+    int sync_rank, sync_world;
+    unsigned int sync_epoch;
 };
+constexpr int kSmDoneIdx = kSmCounterBytes / 4 - 1;          // the grid's exit counter for that (last word of the counter block)
 
 template <typename ACT> struct SmTraits;
 template <> struct SmTraits<__nv_bfloat16> {
@@ -855,6 +860,29 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (tid == 0) SM_TRACE(36);
         sm_fixup<ACT>(p, bias, partial, red_tile, c_first, c_last, tid, kSmConsThreads);
     }
+    if (p.sync_world > 0) {
+        // ===== cross-GPU completion (column-parallel layers): see PeerSync =====
+        sm_cons_sync();                                      // every global store of this CTA has been issued
+        if (tid == 0) {
+            __threadfence_system();                          // ... and is performed, on the peers too, before the count moves
+            const unsigned int old = atomicAdd(counters + kSmDoneIdx, 1u);
+            if (old == gridDim.x - 1u) {
+                counters[kSmDoneIdx] = 0u;                   // clean for the next call
+                __threadfence_system();                      // the other CTAs' stores (observed through the counter) come first
+                for (int r = 0; r < p.sync_world; ++r)
+                    if (r != p.sync_rank)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.sync_flags[r] + p.sync_rank), "r"(p.sync_epoch) : "memory");
+                for (int r = 0; r < p.sync_world; ++r) {
+                    if (r == p.sync_rank) continue;
+                    unsigned int seen = 0, spins = 0;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_flags[p.sync_rank] + r) : "memory");
+                        if ((int)(seen - p.sync_epoch) >= 0 || ++spins > (1u << 28)) break;
+                    }
+                }
+            }
+        }
+    }
 #ifdef QUANTA_SMALL_TRACE
     if (tid == 0) {
         SM_TRACE(37);
@@ -902,8 +930,19 @@ bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const v
 template <typename ACT, int BITS, int NB, bool NF4>
 static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias,
                                 void* const* ys, int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K,
-                                void* workspace, size_t ws_bytes, cudaStream_t st) {
+                                void* workspace, size_t ws_bytes, cudaStream_t st, const PeerSync* sync) {
     SmallParams p;
+    p.sync_world = 0; p.sync_rank = 0; p.sync_epoch = 0u;
+    for (int o = 0; o < kSmMaxOut; ++o) p.sync_flags[o] = nullptr;
+    if (sync) {
+        if (sync->world < 2 || sync->world > kSmMaxOut || sync->rank < 0 || sync->rank >= sync->world) return QUANTA_EINVAL;
+        if ((N + kSmRows - 1) / kSmRows >= kSmDoneIdx) return QUANTA_EUNSUPPORTED;
+        p.sync_world = sync->world; p.sync_rank = sync->rank; p.sync_epoch = sync->epoch;
+        for (int r = 0; r < sync->world; ++r) {
+            if (!sync->flags[r]) return QUANTA_EINVAL;
+            p.sync_flags[r] = static_cast<unsigned int*>(sync->flags[r]);
+        }
+    }
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.m_pad = 8 * NB;
     p.n_tiles = (int)((N + kSmRows - 1) / kSmRows);
@@ -934,7 +973,9 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     if (small_tuning().ctas) {
         n_cta = small_tuning().ctas < n_cta ? small_tuning().ctas : n_cta;
     } else if (p.n_tiles <= sms) {
-        const double w = (BITS == 8 ? 2.0 / 3.0 : 1.0) * (NB == 1 ? 1.0 : 1.3);
+        // the hand-over is a fixed time (~2.7 us); in units of a stage it shrinks as the stage grows (8-bit: 1.5 x the
+        // bytes, M > 8: 1.3 x the consumer time)
+        const double w = (BITS == 8 ? 2.0 / 3.0 : 1.0) * (NB == 1 ? 1.0 : 0.77);
         double best = (double)p.U / n_cta + 3.0 * w;
         for (int k = 1; k * p.n_tiles <= sms && k <= p.S; ++k) {
             const double cost = (double)((p.S + k - 1) / k) + (k > 1 ? 2.2 * w : 0.0);
@@ -1015,20 +1056,21 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
 template <typename ACT, int BITS>
 int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
                       int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
-                      cudaStream_t st, int nf4) {
+                      cudaStream_t st, int nf4, const PeerSync* sync) {
     if (nf4) {
         // 4-bit codes index the NF4 table, `scale` holds abs_max per block, `zp` is not read
         if (BITS != 4) return QUANTA_EINVAL;
-        if (M <= 8) return gemm_small_launch_nb<ACT, 4, 1, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
-        return gemm_small_launch_nb<ACT, 4, 2, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+        if (M <= 8) return gemm_small_launch_nb<ACT, 4, 1, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+        return gemm_small_launch_nb<ACT, 4, 2, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
     }
-    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
-    return gemm_small_launch_nb<ACT, BITS, 2, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st);
+    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+    return gemm_small_launch_nb<ACT, BITS, 2, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
 }
 
 #define QUANTA_SMALL_INST(ACT, BITS)                                                                                    \
     template int gemm_small_launch<ACT, BITS>(const ACT*, const uint8_t*, const float*, const float*, const ACT*, void* const*, \
-                                              int, int64_t, int64_t, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t, int);
+                                              int, int64_t, int64_t, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t, int, \
+                                              const PeerSync*);
 QUANTA_SMALL_INST(__nv_bfloat16, 4)
 QUANTA_SMALL_INST(__nv_bfloat16, 8)
 QUANTA_SMALL_INST(__half, 4)

@@ -70,13 +70,16 @@ def linear_wna16(x, wq, scale, zp, bias=None, bits=4, blocksize=64, out_features
     return y.reshape(*x.shape[:-1], N)
 
 
-def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=64, out_features=None):
+def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=64, out_features=None, sync=None):
     """``linear_wna16`` whose epilogue writes this rank's output columns into every buffer
     of ``outs``: ``y_o[:, col0:col0+N] = x @ dequant(Wq).T + bias`` for each ``y_o``.
 
     outs   (device pointers, ldy): [M, ldy] buffers of x's dtype with the same row pitch —
            the local output and the peer-mapped outputs of the other ranks
-    Returns nothing; the caller synchronises the ranks before reading."""
+    sync   optional (flag_ptrs, rank, world, epoch): synchronise the ranks inside the kernel
+           (``quanta_gemm_wna16_scatter_sync``; decode-sized batches only)
+    Returns True when the ranks were synchronised in the kernel, else False: the caller
+    then synchronises the ranks itself before reading."""
     import ctypes
     _host.require_cuda(x, "x")
     if x.dtype not in (torch.float16, torch.bfloat16):
@@ -89,12 +92,26 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
     M = x2.shape[0]
     ptrs, ldy = outs
     if M == 0 or N == 0:
-        return
+        return False
     _check_weight_args(x, wq, (("scale", scale), ("zero_point", zp)), N, K, bits, blocksize, "linear_wna16_scatter")
     dev = x.device
     if bias is not None and (bias.dtype != x.dtype or bias.device != dev or not bias.is_contiguous()):
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    if sync is not None and M <= 16:
+        flag_ptrs, rank, world, epoch = sync
+        farr = (ctypes.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        with _host.device_guard(dev):
+            ws = _host.gemm_workspace(dev, _host.workspace_bytes(_lib.OP_GEMM, M, N))
+            st = _lib.lib().quanta_gemm_wna16_scatter_sync(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits,
+                                                           scale.data_ptr(), zp.data_ptr(), blocksize,
+                                                           bias.data_ptr() if bias is not None else None, arr, len(ptrs), ldy,
+                                                           col0, M, N, K, ws.data_ptr(), ws.numel(), farr, rank, world,
+                                                           epoch & 0xFFFFFFFF, _host.stream_ptr(dev))
+        if st == 0:
+            return True
+        if st != _lib.E_UNSUPPORTED:
+            _lib.check(st, "quanta_gemm_wna16_scatter_sync")
     with _host.device_guard(dev):
         ws = _host.gemm_workspace(dev, _host.workspace_bytes(_lib.OP_GEMM, M, N))
         st = _lib.lib().quanta_gemm_wna16_scatter(x2.data_ptr(), _host.dtype_code(x2), wq.data_ptr(), bits,
@@ -102,6 +119,7 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
                                                   bias.data_ptr() if bias is not None else None, arr, len(ptrs), ldy,
                                                   col0, M, N, K, ws.data_ptr(), ws.numel(), _host.stream_ptr(dev))
     _lib.check(st, "quanta_gemm_wna16_scatter")
+    return False
 
 
 def linear_nf4a16(x, wq, absmax, bias=None, blocksize=64, out_features=None, in_features=None):

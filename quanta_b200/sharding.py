@@ -99,6 +99,7 @@ class TensorParallelLinear(nn.Module):
         # GPUs; with 2 ranks one store per peer is as fast or faster); "multicast" / "peer" force either
         self.fused_gather = fused_gather if (fused_gather and self.world_size > 1) else False
         self.max_rows = max_rows
+        self.kernel_sync = True             # False: always the separate barrier (A/B measurements)
         self._sym = None
 
     def _apply(self, fn, *args, **kwargs):
@@ -128,7 +129,15 @@ class TensorParallelLinear(nn.Module):
                     mc = int(hdl.multicast_ptr)
             except Exception:                      # noqa: BLE001 - older torch: no multicast query
                 mc = 0
-            self._sym = {"buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs], "turn": 0, "mc": mc}
+            # completion flags for the in-kernel synchronisation of decode-sized batches
+            # (quanta_gemm_wna16_scatter_sync): one unsigned int per peer, zero before the first call on every rank
+            flags = symm.empty((max(self.world_size, 8),), dtype=torch.int32, device=device)
+            flags.zero_()
+            fhdl = symm.rendezvous(flags, grp)
+            torch.cuda.synchronize(device)
+            fhdl.barrier(channel=0)
+            self._sym = {"buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs], "turn": 0, "mc": mc,
+                         "flags": flags, "fhdl": fhdl, "flag_ptrs": [int(p) for p in fhdl.buffer_ptrs], "epoch": 0}
         return self._sym
 
     @torch.no_grad()
@@ -175,8 +184,15 @@ class TensorParallelLinear(nn.Module):
         r0, r1 = self.rows
         # one store per peer, or ONE store to the multicast address that the switch replicates to every rank
         targets = [sym["mc"] + slot] if sym["mc"] else [p + slot for p in sym["ptrs"]]
-        linear_wna16_scatter(x2, self.qweight, self.scale, self.zero_point, self.bias,
-                             (targets, self.out_features), r0, bits=self.bits,
-                             blocksize=self.blocksize, out_features=r1 - r0)
-        sym["hdl"].barrier(channel=0)       # every rank's tiles have landed in this rank's buffer
+        # M <= 16: the ranks meet inside the kernel (its last CTA signals the peers and waits for them), so there is
+        # no barrier kernel behind a GEMM that is itself only ~10 us long; otherwise one barrier on the stream
+        sync = None
+        if self.kernel_sync and M <= 16:
+            sym["epoch"] += 1
+            sync = (sym["flag_ptrs"], self.rank, self.world_size, sym["epoch"])
+        done = linear_wna16_scatter(x2, self.qweight, self.scale, self.zero_point, self.bias,
+                                    (targets, self.out_features), r0, bits=self.bits,
+                                    blocksize=self.blocksize, out_features=r1 - r0, sync=sync)
+        if not done:
+            sym["hdl"].barrier(channel=0)   # every rank's tiles have landed in this rank's buffer
         return sym["buf"][turn, :M]

@@ -31,6 +31,25 @@ for (N, K, M, bits) in [(1024, 512, 33, 4), (896, 1024, 7, 8), (2048, 256, 130, 
             y = lin(xi).clone()
             ref = linear_wna16(xi, *qf, b.to(dev), bits=bits, blocksize=64, out_features=N)
             assert torch.equal(y, ref), f"rank {rank}: N={N} K={K} M={M} bits={bits} fused={fused} turn {it}"
+# decode-sized batches on shapes whose K range is split over several CTAs: the ranks are synchronised INSIDE the kernel
+# (quanta_gemm_wna16_scatter_sync).  Many back-to-back calls with changing inputs and no host synchronisation in
+# between (both output buffers, epoch counting); the fused result must equal the all-gather of the same local GEMMs.
+for (N, K, M, bits) in [(2048, 4096, 1, 4), (4096, 8192, 16, 4), (1024, 2048, 5, 8), (896, 11008, 9, 4)]:
+    w = torch.randn(N, K, generator=g) * 0.02
+    b = torch.randn(N, generator=g) * 0.1
+    x = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    plain = TensorParallelLinear(K, N, bits=bits, bias=True, compute_dtype=torch.bfloat16, fused_gather=False)
+    r0, r1 = plain.rows
+    plain.load_shard(w[r0:r1].to(dev), b[r0:r1].to(dev))
+    for fused in (True, "peer"):
+        lin = TensorParallelLinear(K, N, bits=bits, bias=True, compute_dtype=torch.bfloat16, fused_gather=fused)
+        lin.qweight, lin.scale, lin.zero_point, lin.bias = plain.qweight, plain.scale, plain.zero_point, plain.bias
+        xs = [(x * (1 + 0.25 * it)).contiguous() for it in range(24)]
+        ys = [lin(xi).clone() for xi in xs]                    # 24 calls in a row
+        torch.cuda.synchronize()
+        assert lin._sym["epoch"] == 24, "the in-kernel synchronisation was not used"
+        for it, xi in enumerate(xs):
+            assert torch.equal(ys[it], plain(xi)), f"rank {rank}: N={N} K={K} M={M} bits={bits} fused={fused} call {it}"
 dist.barrier()
 if rank == 0:
     print("TP_OK")
