@@ -973,12 +973,14 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
     if (small_tuning().ctas) {
         n_cta = small_tuning().ctas < n_cta ? small_tuning().ctas : n_cta;
     } else if (p.n_tiles <= sms) {
-        // the hand-over is a fixed time (~2.7 us); in units of a stage it shrinks as the stage grows (8-bit: 1.5 x the
-        // bytes, M > 8: 1.3 x the consumer time)
-        const double w = (BITS == 8 ? 2.0 / 3.0 : 1.0) * (NB == 1 ? 1.0 : 0.77);
-        double best = (double)p.U / n_cta + 3.0 * w;
+        // Costs of the two endings in stage times, fitted to measurements (W4, stage = 0.9 us at M <= 8, 1.3 us above):
+        // an even cut ends on the hand-over AND gives most CTAs two segments; k CTAs per tile end on the hand-over only
+        // (k > 1) or on nothing (k = 1).  They are fixed times, so they shrink in stage units as the stage grows (8-bit).
+        const double f = BITS == 8 ? 2.0 / 3.0 : 1.0;
+        const double h_even = f * (NB == 1 ? 3.05 : 2.3), h_tile = f * (NB == 1 ? 2.1 : 0.85);
+        double best = (double)p.U / n_cta + h_even;
         for (int k = 1; k * p.n_tiles <= sms && k <= p.S; ++k) {
-            const double cost = (double)((p.S + k - 1) / k) + (k > 1 ? 2.2 * w : 0.0);
+            const double cost = (double)((p.S + k - 1) / k) + (k > 1 ? h_tile : 0.0);
             if (cost <= best && p.S % k == 0) { best = cost; n_cta = k * p.n_tiles; }
         }
     }
