@@ -123,6 +123,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) minmax_tensor_partial_kernel(const T* __restrict__ x, int64_t n,
                                                                     float* __restrict__ pmin,
                                                                     float* __restrict__ pmax) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     constexpr int VEC = 16 / sizeof(T);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) minmax_tensor_finalize_kernel(const float
                                                                      const float* __restrict__ pmax, int nparts,
                                                                      int bits, float* scale_out, float* zp_out,
                                                                      float* ws) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     float mn = pmin[0], mx = pmax[0];
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) { mn = min_nan(mn, pmin[i]); mx = max_nan(mx, pmax[i]); }
 #pragma unroll
@@ -197,6 +199,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) minmax_dim0_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                   int rows_per_chunk, float* __restrict__ pmin,
                                                                   float* __restrict__ pmax) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c >= cols) return;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(128) minmax_dim0_partial_generic_kernel(const 
                                                                           int64_t cols, int rows_per_chunk,
                                                                           float* __restrict__ pmin,
                                                                           float* __restrict__ pmax) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
@@ -256,13 +260,17 @@ __global__ void __launch_bounds__(128) minmax_dim0_partial_generic_kernel(const 
 // Reduce the row-chunk partials of each column and emit its parameters; conv B
 // also needs "allclose for ALL channels": every thread ANDs into ws[0]
 // (pre-set to 1 by minmax_dim0_flag_init).
-__global__ void dim0_flag_init_kernel(float* ws, int value) { reinterpret_cast<int*>(ws)[0] = value; }
+__global__ void dim0_flag_init_kernel(float* ws, int value) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
+    reinterpret_cast<int*>(ws)[0] = value;
+}
 
 template <int CONV>
 __global__ void __launch_bounds__(32) minmax_dim0_finalize_kernel(const float* __restrict__ pmin,
                                                                    const float* __restrict__ pmax, int nchunks,
                                                                    int64_t cols, int bits, float* scale_out,
                                                                    float* zp_out, float* ws) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool close = true;
     if (c < cols) {
@@ -289,6 +297,7 @@ __global__ void __launch_bounds__(32) minmax_dim0_finalize_kernel(const float* _
 
 // conv B early-out for per_channel: scale = 1, zp = min for every channel.
 __global__ void dim0_earlyout_params_kernel(int64_t cols, float* scale_out, float* zp_out, const float* ws) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     if (reinterpret_cast<const int*>(ws)[0] == 0) return;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < cols) { scale_out[c] = 1.0f; zp_out[c] = ws[kWsHeaderFloats + c]; }
@@ -1399,6 +1408,7 @@ __global__ void __launch_bounds__(128) quantize_dim0_kernel(const T* __restrict_
                                                             int rows_per_chunk, uint8_t* __restrict__ q_out,
                                                             const float* __restrict__ scale, const float* __restrict__ zp,
                                                             const float* __restrict__ ws) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c >= cols) return;
     constexpr float L = BITS == 8 ? 255.0f : 15.0f;
@@ -1456,6 +1466,7 @@ __global__ void __launch_bounds__(256) quantize_generic_kernel(const T* __restri
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ zp,
                                                                const float* __restrict__ ws) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     constexpr float L = BITS == 8 ? 255.0f : 15.0f;
     constexpr float Q = BITS == 8 ? 127.0f : 7.0f;
     constexpr uint32_t off = (CONV == kConvBSym) ? (BITS == 8 ? 128u : 8u) : 0u;
@@ -1488,6 +1499,7 @@ __global__ void __launch_bounds__(256) quantize_block_generic_kernel(const T* __
                                                                      int64_t block, uint8_t* __restrict__ q_out,
                                                                      float* __restrict__ scale_out,
                                                                      float* __restrict__ zp_out) {
+    pdl_wait();                                            // launched with programmatic stream serialization (launch_pdl)
     constexpr float L = BITS == 8 ? 255.0f : 15.0f;
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1697,23 +1709,23 @@ static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, ui
             const int64_t start = n_rows * kRowElems;
             if (start < n) {
                 int64_t pairs = (n - start + 1) / 2;
-                quantize_generic_kernel<T, BITS, PACK, CONV><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+                launch_pdl(quantize_generic_kernel<T, BITS, PACK, CONV>, dim3((unsigned)((pairs + 255) / 256)), dim3(256), 0, st, 
                     x, start, n, 1, q, scale, zp, ws);
             }
             return cuda_status(cudaGetLastError());
         }
-        minmax_tensor_partial_kernel<T><<<g, 256, 0, st>>>(x, n, pmin, pmax);
+        launch_pdl(minmax_tensor_partial_kernel<T>, g, dim3(256), 0, st, x, n, pmin, pmax);
         if (n_rows > 0) {
             // the streaming kernel finalizes the reduction itself and publishes scale / zp
             int rc = launch_rows_tma<T, BITS, PACK, CONV, false>(x, n_rows, 1, q, scale, zp, ws, g, st);
             if (rc) return rc;
         } else {
-            minmax_tensor_finalize_kernel<CONV><<<1, 256, 0, st>>>(pmin, pmax, g, BITS, scale, zp, ws);
+            launch_pdl(minmax_tensor_finalize_kernel<CONV>, dim3(1), dim3(256), 0, st, pmin, pmax, g, BITS, scale, zp, ws);
         }
         const int64_t start = n_rows * kRowElems;
         if (start < n) {
             int64_t pairs = (n - start + 1) / 2;
-            quantize_generic_kernel<T, BITS, PACK, CONV><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+            launch_pdl(quantize_generic_kernel<T, BITS, PACK, CONV>, dim3((unsigned)((pairs + 255) / 256)), dim3(256), 0, st, 
                 x, start, n, 1, q, scale, zp, ws);
         }
         return cuda_status(cudaGetLastError());
@@ -1732,27 +1744,27 @@ static int quantize_reduced(const T* x, int64_t rows, int64_t cols, int mode, ui
     nchunks = (int)((rows + rpc - 1) / rpc);
     float* pmax = pmin + (int64_t)nchunks * cols;
     const bool fast = (cols % 4 == 0) && aligned16(x) && aligned16(q) && aligned16(ws);
-    if (CONV != kConvA) dim0_flag_init_kernel<<<1, 1, 0, st>>>(ws, 1);
+    if (CONV != kConvA) launch_pdl(dim0_flag_init_kernel, dim3(1), dim3(1), 0, st, ws, 1);
     if (fast) {
         dim3 g((unsigned)((cols / 4 + 127) / 128), nchunks);
-        minmax_dim0_partial_kernel<T><<<g, 128, 0, st>>>(x, rows, cols, rpc, pmin, pmax);
+        launch_pdl(minmax_dim0_partial_kernel<T>, g, dim3(128), 0, st, x, rows, cols, rpc, pmin, pmax);
     } else {
         dim3 g((unsigned)((cols + 127) / 128), nchunks);
-        minmax_dim0_partial_generic_kernel<T><<<g, 128, 0, st>>>(x, rows, cols, rpc, pmin, pmax);
+        launch_pdl(minmax_dim0_partial_generic_kernel<T>, g, dim3(128), 0, st, x, rows, cols, rpc, pmin, pmax);
     }
-    minmax_dim0_finalize_kernel<CONV><<<(unsigned)((cols + 31) / 32), 32, 0, st>>>(pmin, pmax, nchunks, cols, BITS,
+    launch_pdl(minmax_dim0_finalize_kernel<CONV>, dim3((unsigned)((cols + 31) / 32)), dim3(32), 0, st, pmin, pmax, nchunks, cols, BITS,
                                                                                   scale, zp, ws);
-    if (CONV != kConvA) dim0_earlyout_params_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(cols, scale, zp, ws);
+    if (CONV != kConvA) launch_pdl(dim0_earlyout_params_kernel, dim3((unsigned)((cols + 127) / 128)), dim3(128), 0, st, cols, scale, zp, ws);
     if (fast) {
         int qchunks = (int)((rows + 31) / 32);
         if (qchunks > 1024) qchunks = 1024;
         const int qrpc = (int)((rows + qchunks - 1) / qchunks);
         qchunks = (int)((rows + qrpc - 1) / qrpc);
         dim3 g((unsigned)((cols / 4 + 127) / 128), qchunks);
-        quantize_dim0_kernel<T, BITS, PACK, CONV><<<g, 128, 0, st>>>(x, rows, cols, qrpc, q, scale, zp, ws);
+        launch_pdl(quantize_dim0_kernel<T, BITS, PACK, CONV>, g, dim3(128), 0, st, x, rows, cols, qrpc, q, scale, zp, ws);
     } else {
         int64_t pairs = (n + 1) / 2;
-        quantize_generic_kernel<T, BITS, PACK, CONV><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+        launch_pdl(quantize_generic_kernel<T, BITS, PACK, CONV>, dim3((unsigned)((pairs + 255) / 256)), dim3(256), 0, st, 
             x, 0, n, cols, q, scale, zp, ws);
     }
     return cuda_status(cudaGetLastError());
@@ -1768,7 +1780,7 @@ static int quantize_affine_t(const T* x, int64_t rows, int64_t cols, int mode, i
             return launch_rows_tma<T, BITS, PACK, kConvA, true>(x, n / kRowElems, (int)(block / kRowElems), q, scale, zp,
                                                                 ws, 0, st);
         if (PACK && (block & 1)) return QUANTA_EUNSUPPORTED;
-        quantize_block_generic_kernel<T, BITS, PACK><<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(x, nblocks, block, q,
+        launch_pdl(quantize_block_generic_kernel<T, BITS, PACK>, dim3((unsigned)((nblocks + 7) / 8)), dim3(256), 0, st, x, nblocks, block, q,
                                                                                                   scale, zp);
         return cuda_status(cudaGetLastError());
     }
