@@ -977,7 +977,8 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
         // an even cut ends on the hand-over AND gives most CTAs two segments; k CTAs per tile end on the hand-over only
         // (k > 1) or on nothing (k = 1).  They are fixed times, so they shrink in stage units as the stage grows (8-bit).
         const double f = BITS == 8 ? 2.0 / 3.0 : 1.0;
-        const double h_even = f * (NB == 1 ? 3.05 : 2.3), h_tile = f * (NB == 1 ? 2.1 : 0.85);
+        // (M <= 8: k > 1 measured 0.2-0.5 us slower than the even cut wherever the two were close, hence 3.0)
+        const double h_even = f * (NB == 1 ? 3.05 : 2.3), h_tile = f * (NB == 1 ? 3.0 : 0.85);
         double best = (double)p.U / n_cta + h_even;
         for (int k = 1; k * p.n_tiles <= sms && k <= p.S; ++k) {
             const double cost = (double)((p.S + k - 1) / k) + (k > 1 ? h_tile : 0.0);
