@@ -157,6 +157,19 @@ def test_gemm_right_behind_the_kernel_that_wrote_its_weights(bits):
         torch.cuda.synchronize()
         bad += sum(0 if torch.equal(a, b) else 1 for a, b in zip(outs, want))
     assert bad == 0
+    # ... and behind a kernel of another library that writes them (a torch copy: it never releases dependents early,
+    # so the GEMM grid starts only when the copy has completed)
+    q, s, z = quant(ws[0])
+    torch.cuda.synchronize()
+    bad = 0
+    for rep in range(30):
+        q2, s2, z2 = torch.empty_like(q), torch.empty_like(s), torch.empty_like(z)
+        q2.copy_(q); s2.copy_(s); z2.copy_(z)
+        y = linear_wna16(x, q2, s2, z2, None, bits=bits, blocksize=64, out_features=N)
+        q2.zero_()                                         # the next kernel on the stream overwrites the codes
+        torch.cuda.synchronize()
+        bad += 0 if torch.equal(y, want[0]) else 1
+    assert bad == 0
 
 
 def test_cta_pair_multicast_mode():
