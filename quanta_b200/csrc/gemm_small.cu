@@ -790,6 +790,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             sm_sts32(red + (uint32_t)(kq - 1) * red_group + (uint32_t)(((sl * NB + nb) * 4 + q) * 128), tot[sl][nb][q]);
             }
             sm_cons_sync();
+            if (tid == 0) SM_TRACE(29);
             const int n0 = tile * kSmRows;
             if (kq == 0) {
                 // tot[sl][nb][q]: feature n0 + rows[sl][q >> 1], batch row 8 nb + 2 tig + (q & 1)
@@ -846,7 +847,9 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { tot[sl][nb][0] = tot[sl][nb][1] = tot[sl][nb][2] = tot[sl][nb][3] = 0.0f; }
             if (!whole && s1 == S) red_tile = tile;          // this CTA reduces the tile once its stream has ended
-            sm_cons_sync();                                  // red is reused by the next segment; the partial stores are done
+            if (tid == 0) SM_TRACE(30);
+            sm_cons_sync();
+            if (tid == 0) SM_TRACE(31);                                  // red is reused by the next segment; the partial stores are done
             if (!whole && final_seg && s1 != S && tid == 0) sm_contribute(counters, tile);
         }
     }

@@ -42,7 +42,7 @@ st = lib.quanta_debug_small_trace(C.c_void_p(buf.ctypes.data))
 assert st == 0, st
 g0 = buf[:, 38].min()
 names = {32: "producer thread enters", 33: "weight barriers initialised", 34: "producer loop starts", 1: "producer first issue", 2: "producer dep-wait done", 3: "first stage landed", 4: "producer done", 5: "consumers enter", 24: "x warp 0 enters", 25: "x unit 0 staged", 26: "x unit 1 staged", 27: "cons: stage 0 full seen", 28: "cons: x 0 seen",
-         6: "last segment loop end", 7: "walk end", 36: "reducer: contributors seen", 37: "kernel end (tid 0)"}
+         6: "last segment loop end", 29: "epilogue: K quarters met", 30: "epilogue: result stored", 31: "epilogue: CTA synced", 7: "walk end", 36: "reducer: contributors seen", 37: "kernel end (tid 0)"}
 np.set_printoptions(linewidth=200)
 print("globaltimer entry skew (ns): min 0, median %d, max %d;  exit - first entry: median %d, max %d" % (
     np.median(buf[:, 38] - g0), (buf[:, 38] - g0).max(), np.median(buf[:, 39] - g0), (buf[:, 39] - g0).max()))
