@@ -263,11 +263,14 @@ QUANTA_API int quanta_gemm_wna16_scatter(const void* x, int act_dtype, const uin
  * (decode-sized batches: the separate barrier kernel costs as much as the GEMM).
  * peer_flags: host array of `world` device pointers, peer_flags[r] = rank r's
  * flag array of `world` unsigned ints in peer-mapped (symmetric) memory,
- * zero-initialised once; epoch: a counter the caller increments on every call
- * of the layer.  The last CTA of this rank's grid stores `epoch` into
+ * zero-initialised once; epoch_counter: one unsigned int in this rank's own
+ * device memory, zero-initialised once, owned by the layer (the kernel
+ * increments it: replaying the launch from a CUDA graph advances the epoch
+ * like an eager call; every rank must run the same sequence of calls).  The
+ * last CTA of this rank's grid stores the new epoch into
  * peer_flags[r][rank] of every peer after all of the grid's output stores are
  * performed system-wide, and leaves only when peer_flags[rank][r] has reached
- * `epoch` for every r: completion of the kernel on a rank means that every
+ * that epoch for every r: completion of the kernel on a rank means that every
  * rank's columns are in that rank's y.  Returns QUANTA_EUNSUPPORTED when the
  * shape is outside the small-batch kernel (M > 16, block != 64, K % 256 != 0);
  * the caller then falls back to quanta_gemm_wna16_scatter + its own barrier. */
@@ -276,7 +279,7 @@ QUANTA_API int quanta_gemm_wna16_scatter_sync(const void* x, int act_dtype, cons
                               const void* bias, void* const* ys, int n_out, int64_t ldy, int64_t col0,
                               int64_t M, int64_t N, int64_t K,
                               void* workspace, size_t workspace_bytes,
-                              void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream);
+                              void* const* peer_flags, int rank, int world, unsigned int* epoch_counter, void* stream);
 
 /* The same for NF4 weights — Linear4bit's default quant_type="nf4"
  * (nn/linear.py:58): wq nibble-packed NF4 codes [N, K/2], absmax float32

@@ -1190,11 +1190,11 @@ extern "C" int quanta_gemm_wna16_scatter_sync(const void* x, int act_dtype, cons
                                               const float* zp, int64_t block, const void* bias, void* const* ys, int n_out,
                                               int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace,
                                               size_t workspace_bytes, void* const* peer_flags, int rank, int world,
-                                              unsigned int epoch, void* stream) {
-    if (!peer_flags || world < 2 || world > 8 || rank < 0 || rank >= world) return QUANTA_EINVAL;
+                                              unsigned int* epoch_counter, void* stream) {
+    if (!peer_flags || !epoch_counter || world < 2 || world > 8 || rank < 0 || rank >= world) return QUANTA_EINVAL;
     PeerSync sync;
     for (int r = 0; r < 8; ++r) sync.flags[r] = r < world ? peer_flags[r] : nullptr;
-    sync.rank = rank; sync.world = world; sync.epoch = epoch;
+    sync.rank = rank; sync.world = world; sync.epoch_counter = epoch_counter;
     return gemm_scatter_entry(x, act_dtype, wq, bits, scale, zp, block, bias, ys, n_out, ldy, col0, M, N, K, workspace, workspace_bytes,
                               stream, &sync);
 }

@@ -121,7 +121,7 @@ struct SmallParams {
     // tensor-parallel completion inside the kernel (PeerSync, common.cuh); sync_world == 0: off
     unsigned int* sync_flags[kSmMaxOut];
     int sync_rank, sync_world;
-    unsigned int sync_epoch;
+    unsigned int* sync_epoch;   // this rank's call counter (local device memory)
 };
 constexpr int kSmDoneIdx = kSmCounterBytes / 4 - 1;          // the grid's exit counter for that (last word of the counter block)
 
@@ -871,16 +871,18 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const unsigned int old = atomicAdd(counters + kSmDoneIdx, 1u);
             if (old == gridDim.x - 1u) {
                 counters[kSmDoneIdx] = 0u;                   // clean for the next call
+                const unsigned int epoch = *p.sync_epoch + 1u;   // only this thread of this grid touches the counter
+                *p.sync_epoch = epoch;
                 __threadfence_system();                      // the other CTAs' stores (observed through the counter) come first
                 for (int r = 0; r < p.sync_world; ++r)
                     if (r != p.sync_rank)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.sync_flags[r] + p.sync_rank), "r"(p.sync_epoch) : "memory");
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.sync_flags[r] + p.sync_rank), "r"(epoch) : "memory");
                 for (int r = 0; r < p.sync_world; ++r) {
                     if (r == p.sync_rank) continue;
                     unsigned int seen = 0, spins = 0;
                     for (;;) {
                         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_flags[p.sync_rank] + r) : "memory");
-                        if ((int)(seen - p.sync_epoch) >= 0 || ++spins > (1u << 28)) break;
+                        if ((int)(seen - epoch) >= 0 || ++spins > (1u << 28)) break;
                     }
                 }
             }
@@ -935,12 +937,13 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
                                 void* const* ys, int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K,
                                 void* workspace, size_t ws_bytes, cudaStream_t st, const PeerSync* sync) {
     SmallParams p;
-    p.sync_world = 0; p.sync_rank = 0; p.sync_epoch = 0u;
+    p.sync_world = 0; p.sync_rank = 0; p.sync_epoch = nullptr;
     for (int o = 0; o < kSmMaxOut; ++o) p.sync_flags[o] = nullptr;
     if (sync) {
         if (sync->world < 2 || sync->world > kSmMaxOut || sync->rank < 0 || sync->rank >= sync->world) return QUANTA_EINVAL;
         if ((N + kSmRows - 1) / kSmRows >= kSmDoneIdx) return QUANTA_EUNSUPPORTED;
-        p.sync_world = sync->world; p.sync_rank = sync->rank; p.sync_epoch = sync->epoch;
+        if (!sync->epoch_counter) return QUANTA_EINVAL;
+        p.sync_world = sync->world; p.sync_rank = sync->rank; p.sync_epoch = sync->epoch_counter;
         for (int r = 0; r < sync->world; ++r) {
             if (!sync->flags[r]) return QUANTA_EINVAL;
             p.sync_flags[r] = static_cast<unsigned int*>(sync->flags[r]);

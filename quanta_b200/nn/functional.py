@@ -76,7 +76,7 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
 
     outs   (device pointers, ldy): [M, ldy] buffers of x's dtype with the same row pitch —
            the local output and the peer-mapped outputs of the other ranks
-    sync   optional (flag_ptrs, rank, world, epoch): synchronise the ranks inside the kernel
+    sync   optional (flag_ptrs, rank, world, epoch_counter_ptr): synchronise the ranks inside the kernel
            (``quanta_gemm_wna16_scatter_sync``; decode-sized batches only)
     Returns True when the ranks were synchronised in the kernel, else False: the caller
     then synchronises the ranks itself before reading."""
@@ -99,7 +99,7 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
         bias = bias.to(device=dev, dtype=x.dtype).contiguous()
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     if sync is not None and M <= 16:
-        flag_ptrs, rank, world, epoch = sync
+        flag_ptrs, rank, world, epoch_ptr = sync
         farr = (ctypes.c_void_p * len(flag_ptrs))(*flag_ptrs)
         with _host.device_guard(dev):
             ws = _host.gemm_workspace(dev, _host.workspace_bytes(_lib.OP_GEMM, M, N))
@@ -107,7 +107,7 @@ def linear_wna16_scatter(x, wq, scale, zp, bias, outs, col0, bits=4, blocksize=6
                                                            scale.data_ptr(), zp.data_ptr(), blocksize,
                                                            bias.data_ptr() if bias is not None else None, arr, len(ptrs), ldy,
                                                            col0, M, N, K, ws.data_ptr(), ws.numel(), farr, rank, world,
-                                                           epoch & 0xFFFFFFFF, _host.stream_ptr(dev))
+                                                           epoch_ptr, _host.stream_ptr(dev))
         if st == 0:
             return True
         if st != _lib.E_UNSUPPORTED:

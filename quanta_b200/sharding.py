@@ -134,10 +134,11 @@ class TensorParallelLinear(nn.Module):
             flags = symm.empty((max(self.world_size, 8),), dtype=torch.int32, device=device)
             flags.zero_()
             fhdl = symm.rendezvous(flags, grp)
+            counter = torch.zeros(1, dtype=torch.int32, device=device)      # this rank's call counter (the kernel increments it)
             torch.cuda.synchronize(device)
             fhdl.barrier(channel=0)
             self._sym = {"buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs], "turn": 0, "mc": mc,
-                         "flags": flags, "fhdl": fhdl, "flag_ptrs": [int(p) for p in fhdl.buffer_ptrs], "epoch": 0}
+                         "flags": flags, "fhdl": fhdl, "flag_ptrs": [int(p) for p in fhdl.buffer_ptrs], "counter": counter, "epoch": 0}
         return self._sym
 
     @torch.no_grad()
@@ -188,8 +189,8 @@ class TensorParallelLinear(nn.Module):
         # no barrier kernel behind a GEMM that is itself only ~10 us long; otherwise one barrier on the stream
         sync = None
         if self.kernel_sync and M <= 16:
-            sym["epoch"] += 1
-            sync = (sym["flag_ptrs"], self.rank, self.world_size, sym["epoch"])
+            sym["epoch"] += 1                                       # host-side count of synchronised calls (tests)
+            sync = (sym["flag_ptrs"], self.rank, self.world_size, sym["counter"].data_ptr())
         done = linear_wna16_scatter(x2, self.qweight, self.scale, self.zero_point, self.bias,
                                     (targets, self.out_features), r0, bits=self.bits,
                                     blocksize=self.blocksize, out_features=r1 - r0, sync=sync)

@@ -50,6 +50,34 @@ for (N, K, M, bits) in [(2048, 4096, 1, 4), (4096, 8192, 16, 4), (1024, 2048, 5,
         assert lin._sym["epoch"] == 24, "the in-kernel synchronisation was not used"
         for it, xi in enumerate(xs):
             assert torch.equal(ys[it], plain(xi)), f"rank {rank}: N={N} K={K} M={M} bits={bits} fused={fused} call {it}"
+# the same under CUDA-graph replay: the epoch of the in-kernel synchronisation lives in device memory and advances with
+# every replayed launch (a host-side epoch would be frozen into the graph and the ranks would stop meeting)
+N, K, M, bits = 2048, 4096, 4, 4
+w = torch.randn(N, K, generator=g) * 0.02
+xin = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+plain = TensorParallelLinear(K, N, bits=bits, bias=False, compute_dtype=torch.bfloat16, fused_gather=False)
+r0, r1 = plain.rows
+plain.load_shard(w[r0:r1].to(dev))
+lin = TensorParallelLinear(K, N, bits=bits, bias=False, compute_dtype=torch.bfloat16, fused_gather=True)
+lin.qweight, lin.scale, lin.zero_point = plain.qweight, plain.scale, plain.zero_point
+xbuf = xin.clone()
+for _ in range(2):
+    lin(xbuf)                                              # symmetric buffers, workspaces exist before capture
+torch.cuda.synchronize()
+dist.barrier()
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph, stream=side):
+    outs = [lin(xbuf * (1.0 + 0.5 * j)).clone() for j in range(4)]
+for rep in range(6):
+    xbuf.copy_(xin * (1.0 + rep))
+    graph.replay()
+    torch.cuda.synchronize()
+    for j in range(4):
+        want = plain((xin * (1.0 + rep)) * (1.0 + 0.5 * j))
+        assert torch.equal(outs[j], want), f"rank {rank}: graph replay {rep}, call {j}"
+assert int(lin._sym["counter"].item()) == 2 + 4 * 6, int(lin._sym["counter"].item())
 dist.barrier()
 if rank == 0:
     print("TP_OK")
