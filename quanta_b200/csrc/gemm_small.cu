@@ -866,25 +866,33 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (p.sync_world > 0) {
         // ===== cross-GPU completion (column-parallel layers): see PeerSync =====
         sm_cons_sync();                                      // every global store of this CTA has been issued
-        if (tid == 0) {
-            __threadfence_system();                          // ... and is performed, on the peers too, before the count moves
-            const unsigned int old = atomicAdd(counters + kSmDoneIdx, 1u);
-            if (old == gridDim.x - 1u) {
-                counters[kSmDoneIdx] = 0u;                   // clean for the next call
-                const unsigned int epoch = *p.sync_epoch + 1u;   // only this thread of this grid touches the counter
-                *p.sync_epoch = epoch;
+        if (warp == 0) {
+            unsigned int last = 0u, epoch = 0u;
+            if (lane == 0) {
+                __threadfence_system();                      // ... and is performed, on the peers too, before the count moves
+                const unsigned int old = atomicAdd(counters + kSmDoneIdx, 1u);
+                if (old == gridDim.x - 1u) {
+                    last = 1u;
+                    counters[kSmDoneIdx] = 0u;               // clean for the next call
+                    epoch = *p.sync_epoch + 1u;              // only this thread of this grid touches the counter
+                    *p.sync_epoch = epoch;
+                }
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            epoch = __shfl_sync(0xffffffffu, epoch, 0);
+            if (last) {
+                // one lane per peer: all signals leave together and all peers are polled together (one NVLink round trip
+                // instead of world - 1 of them)
                 __threadfence_system();                      // the other CTAs' stores (observed through the counter) come first
-                for (int r = 0; r < p.sync_world; ++r)
-                    if (r != p.sync_rank)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.sync_flags[r] + p.sync_rank), "r"(epoch) : "memory");
-                for (int r = 0; r < p.sync_world; ++r) {
-                    if (r == p.sync_rank) continue;
+                if (lane < p.sync_world && lane != p.sync_rank) {
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.sync_flags[lane] + p.sync_rank), "r"(epoch) : "memory");
                     unsigned int seen = 0, spins = 0;
                     for (;;) {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_flags[p.sync_rank] + r) : "memory");
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_flags[p.sync_rank] + lane) : "memory");
                         if ((int)(seen - epoch) >= 0 || ++spins > (1u << 28)) break;
                     }
                 }
+                __syncwarp();
             }
         }
     }

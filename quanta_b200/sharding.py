@@ -99,7 +99,10 @@ class TensorParallelLinear(nn.Module):
         # GPUs; with 2 ranks one store per peer is as fast or faster); "multicast" / "peer" force either
         self.fused_gather = fused_gather if (fused_gather and self.world_size > 1) else False
         self.max_rows = max_rows
-        self.kernel_sync = True             # False: always the separate barrier (A/B measurements)
+        # True: for M <= 16 the ranks meet inside the GEMM kernel (quanta_gemm_wna16_scatter_sync) instead of in a barrier
+        # kernel behind it.  Measured 1.5-2 us SLOWER (8 GPUs, M = 16: 17.9 vs 16.4 us; 2 GPUs: 21.3 vs 19.8): every CTA
+        # pays a system-scope fence before the exit counter, where the kernel boundary flushes for free.  Off.
+        self.kernel_sync = False
         self._sym = None
 
     def _apply(self, fn, *args, **kwargs):

@@ -43,6 +43,7 @@ for (N, K, M, bits) in [(2048, 4096, 1, 4), (4096, 8192, 16, 4), (1024, 2048, 5,
     plain.load_shard(w[r0:r1].to(dev), b[r0:r1].to(dev))
     for fused in (True, "peer"):
         lin = TensorParallelLinear(K, N, bits=bits, bias=True, compute_dtype=torch.bfloat16, fused_gather=fused)
+        lin.kernel_sync = True                                 # off by default (no faster): exercised here
         lin.qweight, lin.scale, lin.zero_point, lin.bias = plain.qweight, plain.scale, plain.zero_point, plain.bias
         xs = [(x * (1 + 0.25 * it)).contiguous() for it in range(24)]
         ys = [lin(xi).clone() for xi in xs]                    # 24 calls in a row
@@ -59,6 +60,7 @@ plain = TensorParallelLinear(K, N, bits=bits, bias=False, compute_dtype=torch.bf
 r0, r1 = plain.rows
 plain.load_shard(w[r0:r1].to(dev))
 lin = TensorParallelLinear(K, N, bits=bits, bias=False, compute_dtype=torch.bfloat16, fused_gather=True)
+lin.kernel_sync = True
 lin.qweight, lin.scale, lin.zero_point = plain.qweight, plain.scale, plain.zero_point
 xbuf = xin.clone()
 for _ in range(2):

@@ -77,10 +77,16 @@ def tp_rows(device, rank, world, pk, torch_mod, dist, Q, reps=20):
             us_local = graph_us(lambda: lin.local_matmul(x))
             us_nccl = graph_us(lambda: lin(x))
             us_fused = graph_us(lambda: linf(x))
+            # the same with the ranks' completion inside the kernel (M <= 16; off by default: it measures slower)
+            us_fused_kernel_sync = None
+            if M <= 16:
+                linf.kernel_sync = True
+                us_fused_kernel_sync = graph_us(lambda: linf(x))
+                linf.kernel_sync = False
             flops = 2.0 * M * No * Ki
             sent = M * (r1 - r0) * 2
             rows.append({"op": "tp_linear W4A16", "N": No, "K": Ki, "M": M, "world": world,
-                         "us_local_gemm": round(us_local, 2), "us_nccl_gather": round(us_nccl, 2), "us_fused_gather": round(us_fused, 2),
+                         "us_local_gemm": round(us_local, 2), "us_nccl_gather": round(us_nccl, 2), "us_fused_gather": round(us_fused, 2), "us_fused_gather_kernel_sync": (round(us_fused_kernel_sync, 2) if us_fused_kernel_sync is not None else None),
                          "fused_over_local": round(us_fused / us_local, 3), "TFLOPs_fused": round(flops / us_fused / 1e6, 1),
                          "gather_mode": "multicast" if world >= 4 else "peer stores",
                          "nvlink_bytes_sent_per_rank": sent if world >= 4 else sent * (world - 1),
