@@ -281,6 +281,15 @@ QUANTA_API int quanta_gemm_wna16_scatter_sync(const void* x, int act_dtype, cons
                               void* workspace, size_t workspace_bytes,
                               void* const* peer_flags, int rank, int world, unsigned int* epoch_counter, void* stream);
 
+/* The cross-rank barrier behind quanta_gemm_wna16_scatter as one tiny kernel
+ * that overlaps with the NEXT layer: it is launched with programmatic stream
+ * serialization and releases its dependents at once, so the next GEMM's weight
+ * stream starts while the ranks are still meeting; that GEMM's activation
+ * loads and writes wait for the barrier.  peer_flags / epoch_counter as in
+ * quanta_gemm_wna16_scatter_sync (the two may share them).                   */
+QUANTA_API int quanta_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int* epoch_counter,
+                                   void* stream);
+
 /* The same for NF4 weights — Linear4bit's default quant_type="nf4"
  * (nn/linear.py:58): wq nibble-packed NF4 codes [N, K/2], absmax float32
  * [N, K/block] (quanta_quantize_nf4 with block | K, block % 64 == 0);

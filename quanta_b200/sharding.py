@@ -103,6 +103,7 @@ class TensorParallelLinear(nn.Module):
         # kernel behind it.  Measured 1.5-2 us SLOWER (8 GPUs, M = 16: 17.9 vs 16.4 us; 2 GPUs: 21.3 vs 19.8): every CTA
         # pays a system-scope fence before the exit counter, where the kernel boundary flushes for free.  Off.
         self.kernel_sync = False
+        self.own_barrier = True             # False: torch's symmetric-memory barrier kernel (A/B measurements)
         self._sym = None
 
     def _apply(self, fn, *args, **kwargs):
@@ -198,5 +199,16 @@ class TensorParallelLinear(nn.Module):
                                     (targets, self.out_features), r0, bits=self.bits,
                                     blocksize=self.blocksize, out_features=r1 - r0, sync=sync)
         if not done:
-            sym["hdl"].barrier(channel=0)   # every rank's tiles have landed in this rank's buffer
+            # every rank's tiles have landed in this rank's buffer: one tiny kernel (quanta_peer_barrier) that lets the
+            # NEXT layer's weight stream start while the ranks are still meeting
+            if self.own_barrier:
+                import ctypes
+                from . import _host, _lib
+                farr = (ctypes.c_void_p * len(sym["flag_ptrs"]))(*sym["flag_ptrs"])
+                with _host.device_guard(x2.device):
+                    st = _lib.lib().quanta_peer_barrier(farr, self.rank, self.world_size, sym["counter"].data_ptr(),
+                                                        _host.stream_ptr(x2.device))
+                _lib.check(st, "quanta_peer_barrier")
+            else:
+                sym["hdl"].barrier(channel=0)
         return sym["buf"][turn, :M]

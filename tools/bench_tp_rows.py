@@ -83,10 +83,14 @@ def tp_rows(device, rank, world, pk, torch_mod, dist, Q, reps=20):
                 linf.kernel_sync = True
                 us_fused_kernel_sync = graph_us(lambda: linf(x))
                 linf.kernel_sync = False
+            # the same with torch's symmetric-memory barrier kernel instead of quanta_peer_barrier
+            linf.own_barrier = False
+            us_fused_torch_barrier = graph_us(lambda: linf(x))
+            linf.own_barrier = True
             flops = 2.0 * M * No * Ki
             sent = M * (r1 - r0) * 2
             rows.append({"op": "tp_linear W4A16", "N": No, "K": Ki, "M": M, "world": world,
-                         "us_local_gemm": round(us_local, 2), "us_nccl_gather": round(us_nccl, 2), "us_fused_gather": round(us_fused, 2), "us_fused_gather_kernel_sync": (round(us_fused_kernel_sync, 2) if us_fused_kernel_sync is not None else None),
+                         "us_local_gemm": round(us_local, 2), "us_nccl_gather": round(us_nccl, 2), "us_fused_gather": round(us_fused, 2), "us_fused_gather_torch_barrier": round(us_fused_torch_barrier, 2), "us_fused_gather_kernel_sync": (round(us_fused_kernel_sync, 2) if us_fused_kernel_sync is not None else None),
                          "fused_over_local": round(us_fused / us_local, 3), "TFLOPs_fused": round(flops / us_fused / 1e6, 1),
                          "gather_mode": "multicast" if world >= 4 else "peer stores",
                          "nvlink_bytes_sent_per_rank": sent if world >= 4 else sent * (world - 1),
