@@ -17,7 +17,9 @@ the only exchange step on the path — in one of two ways:
   store to the buffer's NVSwitch multicast address, which the switch replicates
   to all ranks — or, without multicast (``fused_gather="peer"``), one store per
   peer-mapped buffer.  The gather overlaps the math tile by tile and the only
-  thing after the kernel is a cross-rank barrier on the stream.
+  thing after the kernel is a cross-rank barrier on the stream: one warp
+  (``quanta_peer_barrier``) that releases its own dependents at once, so the
+  next layer's weight stream starts while the ranks are still meeting.
 
 One process per GPU; ``torch.distributed`` is plumbing only.
 """
