@@ -1,41 +1,41 @@
-// W4A16 / W8A16 dequantize-then-matmul for decode-sized batches (M <= 16; rows G1/G2 of SURVEY §8):
-//     y[M,N] = x[M,K] . dequant(Wq)[N,K]^T + bias,   Wq blockwise-64 along K (convention A).
+// W4A16 / W8A16 / NF4A16 dequantize-then-matmul for decode-sized batches (M <= 16; rows G1/G2 and N1 of SURVEY §8):
+//     y[M,N] = x[M,K] . dequant(Wq)[N,K]^T + bias,   Wq blockwise-64 along K (convention A) or NF4 codes + abs_max.
 //
 // At these batch sizes the op is a pure weight stream (5.7 us of HBM time for a
 // 4096 x 14336 W4 matrix), so the kernel is built around the stream and keeps everything else
 // off its critical path:
 //
-//   * one persistent CTA per SM.  A producer thread keeps a ring of TMA stages full: SWIZZLE_128B
-//     tiles of [128 rows x 128 B] codes, the step's [128 x 4] scale / zero-point tiles and the step's
-//     activations [m_pad x 256] all on one mbarrier.  It starts before the rest of the CTA is set up
-//     and requests only three stages until the first one has landed (the TMA unit works on all of
-//     its outstanding copies at once: eight stages requested together by 148 SMs all complete
-//     together, ~4.5 K cycles later).  The (row tile, 256-K step) units are cut into equal
-//     contiguous ranges, one per CTA (stream-K), so every SM streams for the same time whatever
-//     the shape;
-//   * 16 consumer warps drain the ring (warp = 32 weight rows x one 64-K block of every step, so
-//     a B fragment read from shared memory serves two row slabs).  Codes are never dequantized one
-//     by one: LOP3 drops a nibble pair into the mantissas of the 16-bit constant 128.0 (bf16) /
-//     1024.0 (fp16) — exact integers C + n — and the warp-level tensor-core MMA (mma.sync m16n8k16,
-//     fp32 accumulate) forms raw = sum_k (C + n_k) x_k over one 64-K block; scale and zero-point are
-//     applied once per block on the accumulators:
+//   * one persistent CTA per SM.  A producer thread keeps a ring of TMA stages full.  A stage is 256 BYTES of codes
+//     per weight row — two SWIZZLE_128B boxes of [128 rows x 128 B] — plus the stage's [128 x kBlk] scale and
+//     zero-point tiles (kBlk = 8 blocks of 64 K for 4-bit codes, 4 for 8-bit), all on one mbarrier: HBM serves
+//     256-byte row pieces at its full rate, 128-byte ones at ~75 % of it (SmGeom).  The producer touches weights only,
+//     so it never waits for the previous kernel (programmatic dependent launch; see pdl_wait in common.cuh for why
+//     that is sound).  It requests `window` stages until the first one has landed (the TMA unit works on all of its
+//     outstanding copies at once), then keeps the whole ring in flight.  The (row tile, stage) units are cut into
+//     contiguous ranges, one per CTA (stream-K); how many CTAs is a cost model on the host (gemm_small_launch_nb);
+//   * 16 consumer warps drain the ring (warp = 32 weight rows x kBpw 64-K blocks of every stage, so a B fragment
+//     read from shared memory serves two row slabs).  Codes are never dequantized one by one: LOP3 drops a nibble
+//     pair into the mantissas of the 16-bit constant 128.0 (bf16) / 1024.0 (fp16) — exact integers C + n — and the
+//     warp-level tensor-core MMA (mma.sync m16n8k16, fp32 accumulate) forms raw = sum_k (C + n_k) x_k over one 64-K
+//     block; scale and zero-point are applied once per block on the accumulators:
 //         y += s * raw + (z - C s) * sum_k x_k
-//     i.e. 7 integer instructions per 8 weights + 2 FMAs per accumulator, instead of 19
-//     instructions per 8 weights for an element-wise dequantization.  The MMA's K order is free as
-//     long as both operands agree, so x is staged in the order the LOP3 pairs come out
-//     (k0,k4 | k1,k5 | k2,k6 | k3,k7) and no PRMT is needed.  8-bit codes go through
-//     PRMT -> fp32 (32768 + q) -> q -> packed 16-bit, exact as well;
-//   * four staging warps turn the raw activations of a stage into MMA fragment order plus the
-//     per-block sums of x, in a 4-slot ring of their own (full / empty mbarriers), so the
-//     consumers' instruction stream is the weight path only;
-//   * a CTA that covers only part of a row tile's K range stores an fp32 partial and bumps the
-//     tile's counter with ONE fire-and-forget release; the CTA that owns the tile's last K steps
-//     is its reducer: once its own stream has ended it acquires the counter, sums the partials in
-//     CTA order (deterministic), adds the bias and writes y — to every output buffer of a
-//     tensor-parallel call (peer-mapped buffers over NVLink).  Nobody pays an atomic round trip
-//     between two fences at the end of the kernel (measured 5-9 K cycles per CTA); when a range
-//     holds whole tiles its partial segments are processed first, so the kernel ends on a plain
-//     store of y.
+//     i.e. 7 integer instructions per 8 weights + 2 FMAs per accumulator, instead of 19 instructions per 8 weights
+//     for an element-wise dequantization.  The MMA's K order is free as long as both operands agree, so x is staged
+//     in the order the LOP3 pairs come out (k0,k4 | k1,k5 | k2,k6 | k3,k7) and no PRMT is needed.  8-bit codes go
+//     through PRMT -> fp32 (32768 + q) -> q -> packed 16-bit, exact as well; NF4 codes through a byte -> level-pair
+//     table in shared memory (one copy per lane), y += abs_max * raw;
+//   * four staging warps read the stage's activations straight from global memory (L2), two to six units ahead in
+//     registers, and write MMA fragment order plus the per-block sums of x into a ring of their own (full / empty
+//     mbarriers), so the consumers' instruction stream is the weight path only and reads shared memory only;
+//   * a CTA that covers only part of a row tile's K range stores an fp32 partial and bumps the tile's counter with
+//     ONE fire-and-forget release; the CTA that owns the tile's last K steps is its reducer: once its own stream has
+//     ended it acquires the counter, sums the partials in CTA order (deterministic), adds the bias and writes y — to
+//     every output buffer of a tensor-parallel call (peer-mapped buffers over NVLink).  Nobody pays an atomic round
+//     trip between two fences at the end of the kernel (measured 5-9 K cycles per CTA); when a range holds whole
+//     tiles its partial segments are processed first, so the kernel ends on a plain store of y;
+//   * no integer division anywhere in the kernel: unit ranges are c q + min(c, r), u / S a multiplication by a
+//     host-computed reciprocal (a 32-bit division is ~100 instructions; they used to sit in every role's prologue
+//     and cost 1.7 us per call).
 //
 // The products use the exact fp32 value q*s + z of the weight (the tcgen05 path in gemm.cu rounds it
 // to the activation type first, like the reference's `.to(x.dtype)`); the difference is far inside
