@@ -51,8 +51,10 @@ namespace quanta {
 constexpr int kSmRows = 128;               // weight rows per tile
 constexpr int kSmConsWarps = 16;           // warp w: rows 32 (w & 3) .. +32, block (w >> 2) of every step
 constexpr int kSmConsThreads = 32 * kSmConsWarps;
-constexpr int kSmXWarps = 4;               // activation staging warps
-constexpr int kSmThreads = kSmConsThreads + 64 + 32 * kSmXWarps;   // + producer warp + publisher warp + staging warps
+// Activation staging warps: 4 — or 2 for a single batch row: 20 warps instead of 22 is one warp-allocation granule less,
+// 96 instead of 80 registers per thread for the consumers, and two warps stage one row of x with time to spare
+// (M = 1: 11.9 -> 11.8 / 11.4 -> 11.1 us W4, 16.2 -> 15.8 W8, 14.1 -> 13.6 NF4; at M = 8 two warps are too few: 14.1 us).
+constexpr int sm_threads(int xw) { return kSmConsThreads + 64 + 32 * xw; }   // consumers + producer + publisher + staging warps
 constexpr int kSmKGran = 256;              // K must be a multiple of this (16-byte scale rows; a partial last step is zero-filled)
 constexpr int kSmMaxRing = 8;
 constexpr int kSmMaxXRing = 4;             // activation slots (one stage each)
@@ -342,14 +344,15 @@ __device__ __forceinline__ void sm_fixup(const SmallParams& p, const ACT* __rest
     }
 }
 
-template <typename ACT, int BITS, int NB, bool NF4>
-__global__ void __launch_bounds__(kSmThreads, 1)
+template <typename ACT, int BITS, int NB, bool NF4, int XW>
+__global__ void __launch_bounds__(sm_threads(XW), 1)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
                   const __grid_constant__ CUtensorMap tmap_z, const ACT* __restrict__ x, const ACT* __restrict__ bias,
                   unsigned int* __restrict__ counters, float* __restrict__ partial, const __grid_constant__ SmallParams p) {
     using T = SmTraits<ACT>;
     using G = SmGeom<BITS, NF4>;
     static_assert(!NF4 || BITS == 4, "NF4 codes are 4-bit");
+    constexpr int kSmXWarps = XW, kSmThreads = sm_threads(XW);
     extern __shared__ __align__(1024) uint8_t sm_raw[];
 
     const uint32_t smem = smem_u32(sm_raw);
@@ -912,16 +915,17 @@ extern "C" __attribute__((visibility("default"))) int quanta_debug_small_trace(l
 
 // ---- host side --------------------------------------------------------------
 
-struct SmallTuning { int ring; int max_m; int ctas; int dbg; int pdl; int xring; int window; };
+struct SmallTuning { int ring; int max_m; int ctas; int dbg; int pdl; int xring; int window; int xw2; };
 static SmallTuning small_tuning() {
     static const SmallTuning t = []() {
-        SmallTuning v{0, 16, 0, 0, 1, 0, kSmStartWindow};
+        SmallTuning v{0, 16, 0, 0, 1, 0, kSmStartWindow, 1};
         if (const char* e = getenv("QUANTA_B200_SMALL_RING")) { int s = atoi(e); if (s >= 2 && s <= kSmMaxRing) v.ring = s; }
         if (const char* e = getenv("QUANTA_B200_SMALL_MAX_M")) { int m = atoi(e); if (m >= 0 && m <= 16) v.max_m = m; }
         if (const char* e = getenv("QUANTA_B200_SMALL_CTAS")) { int c = atoi(e); if (c >= 1 && c <= kNumSMs) v.ctas = c; }
         if (const char* e = getenv("QUANTA_B200_SMALL_DBG")) v.dbg = atoi(e);
         if (const char* e = getenv("QUANTA_B200_SMALL_PDL")) v.pdl = atoi(e) != 0;
         if (const char* e = getenv("QUANTA_B200_SMALL_XRING")) { int s = atoi(e); if (s >= 2 && s <= kSmMaxXRing) v.xring = s; }
+        if (const char* e = getenv("QUANTA_B200_SMALL_XW2")) v.xw2 = atoi(e) != 0;
         if (const char* e = getenv("QUANTA_B200_SMALL_WINDOW")) { int s = atoi(e); if (s >= 1 && s <= kSmMaxRing) v.window = s; }
         return v;
     }();
@@ -940,7 +944,7 @@ bool gemm_small_eligible(int64_t M, int64_t N, int64_t K, int64_t block, const v
     return true;
 }
 
-template <typename ACT, int BITS, int NB, bool NF4>
+template <typename ACT, int BITS, int NB, bool NF4, int XW>
 static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias,
                                 void* const* ys, int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K,
                                 void* workspace, size_t ws_bytes, cudaStream_t st, const PeerSync* sync) {
@@ -1054,11 +1058,11 @@ static int gemm_small_launch_nb(const ACT* x, const uint8_t* wq, const float* sc
                             CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
 
-    auto kern = gemm_small_kernel<ACT, BITS, NB, NF4>;
+    auto kern = gemm_small_kernel<ACT, BITS, NB, NF4, XW>;
     if (int e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.G);
-    cfg.blockDim = dim3(kSmThreads);
+    cfg.blockDim = dim3(sm_threads(XW));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1074,14 +1078,17 @@ template <typename ACT, int BITS>
 int gemm_small_launch(const ACT* x, const uint8_t* wq, const float* scale, const float* zp, const ACT* bias, void* const* ys,
                       int n_out, int64_t ldy, int64_t col0, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
                       cudaStream_t st, int nf4, const PeerSync* sync) {
+    const bool one = M == 1 && small_tuning().xw2;           // a single batch row: two staging warps (see sm_threads)
     if (nf4) {
         // 4-bit codes index the NF4 table, `scale` holds abs_max per block, `zp` is not read
         if (BITS != 4) return QUANTA_EINVAL;
-        if (M <= 8) return gemm_small_launch_nb<ACT, 4, 1, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
-        return gemm_small_launch_nb<ACT, 4, 2, true>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+        if (one) return gemm_small_launch_nb<ACT, 4, 1, true, 2>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+        if (M <= 8) return gemm_small_launch_nb<ACT, 4, 1, true, 4>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+        return gemm_small_launch_nb<ACT, 4, 2, true, 4>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
     }
-    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
-    return gemm_small_launch_nb<ACT, BITS, 2, false>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+    if (one) return gemm_small_launch_nb<ACT, BITS, 1, false, 2>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+    if (M <= 8) return gemm_small_launch_nb<ACT, BITS, 1, false, 4>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
+    return gemm_small_launch_nb<ACT, BITS, 2, false, 4>(x, wq, scale, zp, bias, ys, n_out, ldy, col0, M, N, K, workspace, ws_bytes, st, sync);
 }
 
 #define QUANTA_SMALL_INST(ACT, BITS)                                                                                    \
