@@ -194,7 +194,7 @@ class TensorParallelLinear(nn.Module):
         # M <= 16: the ranks meet inside the kernel (its last CTA signals the peers and waits for them), so there is
         # no barrier kernel behind a GEMM that is itself only ~10 us long; otherwise one barrier on the stream
         sync = None
-        if self.kernel_sync and M <= 16:
+        if self.kernel_sync and M <= 16 and self.world_size <= 8:
             sym["epoch"] += 1                                       # host-side count of synchronised calls (tests)
             sync = (sym["flag_ptrs"], self.rank, self.world_size, sym["counter"].data_ptr())
         done = linear_wna16_scatter(x2, self.qweight, self.scale, self.zero_point, self.bias,
@@ -203,7 +203,7 @@ class TensorParallelLinear(nn.Module):
         if not done:
             # every rank's tiles have landed in this rank's buffer: one tiny kernel (quanta_peer_barrier) that lets the
             # NEXT layer's weight stream start while the ranks are still meeting
-            if self.own_barrier:
+            if self.own_barrier and self.world_size <= 8:
                 import ctypes
                 from . import _host, _lib
                 farr = (ctypes.c_void_p * len(sym["flag_ptrs"]))(*sym["flag_ptrs"])
