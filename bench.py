@@ -332,6 +332,43 @@ def secondary_single_gpu(device, pk, torch, Q):
             return torch.randint(0, 16, (n,), device=device, dtype=torch.uint8, generator=g)
         stream_case("pack_4bit_tensor (P1)", shape, n * 1.5, codes, lambda c: Q.pack_4bit_tensor(c), max(copies, 12))
 
+    # config 4: LLM.int8()-style outlier split on OPT-6.7B shapes against an int8 tensor peak measured here (cuBLASLt)
+    try:
+        from quanta_b200.nn import int8_outlier_matmul, rowwise_quantize_sym
+        a8 = torch.randint(-127, 127, (8192, 8192), device=device, dtype=torch.int8)
+        b8 = torch.randint(-127, 127, (8192, 8192), device=device, dtype=torch.int8).t()
+        for _ in range(3):
+            torch._int_mm(a8, b8)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a8, b8); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        int8_peak = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a8, b8
+        out["outlier"] = [{"int8_tensor_peak_TOPs": round(int8_peak, 1), "how": "torch._int_mm (cuBLASLt int8) 8192^3, best of 6"}]
+        cols = [7, 513, 1024, 2049, 3071, 4000]
+        for (N, K) in ((4096, 4096), (16384, 4096), (4096, 16384)):
+            copies = max(3, int(300e6 // (N * K)) + 1)
+            wq = [rowwise_quantize_sym(torch.empty(N, K, device=device).normal_(0.0, 0.02)) for _ in range(copies)]
+            for M in (1, 16, 256, 2048):
+                x = torch.randn(M, K, device=device)
+                x[:, cols] *= 20.0
+                x = x.to(torch.bfloat16)
+                us = graph_time_us(lambda i: int8_outlier_matmul(x, wq[i % copies][0], wq[i % copies][1], threshold=6.0), 12, torch)
+                launches += 12 * 4
+                flops = 2.0 * M * N * K
+                nbytes = N * K + 4 * N + 2 * M * K + 2 * M * N
+                t_hbm, t_tc = nbytes / HBM / 1e3, flops / int8_peak / 1e6
+                out["outlier"].append({"op": "int8_outlier_matmul", "N": N, "K": K, "M": M, "us": round(us, 2),
+                                       "TOPs": round(flops / us / 1e6, 1), "bound": "hbm" if t_hbm >= t_tc else "tensor(int8)",
+                                       "frac": round(max(t_hbm, t_tc) / us, 3)})
+            del wq
+            torch.cuda.empty_cache()
+    except Exception as ex:                                  # noqa: BLE001 - the contract line must not depend on this row
+        out["outlier"] = [{"skipped": "%s: %s" % (type(ex).__name__, ex)}]
+
     # the blockwise dequantize as ONE launch over a decoder layer's 7 matrices (quanta_dequantize_block_batch)
     layer = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
     elems = sum(a * b for (a, b) in layer)
