@@ -25,9 +25,13 @@ One process per GPU; ``torch.distributed`` is plumbing only.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+
+from . import _host, _lib
 
 
 def row_shard(n_rows, world_size, rank, multiple=1):
@@ -204,8 +208,6 @@ class TensorParallelLinear(nn.Module):
             # every rank's tiles have landed in this rank's buffer: one tiny kernel (quanta_peer_barrier) that lets the
             # NEXT layer's weight stream start while the ranks are still meeting
             if self.own_barrier and self.world_size <= 8:
-                import ctypes
-                from . import _host, _lib
                 farr = (ctypes.c_void_p * len(sym["flag_ptrs"]))(*sym["flag_ptrs"])
                 with _host.device_guard(x2.device):
                     st = _lib.lib().quanta_peer_barrier(farr, self.rank, self.world_size, sym["counter"].data_ptr(),
